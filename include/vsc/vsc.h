@@ -1,0 +1,195 @@
+/* vsc.h -- C ABI of the B200-native hot path of Interactive Temporal Video Consistency.
+ *
+ * One shared library (libvsc_b200.so, hand-written CUDA for sm_100a) exports exactly these
+ * symbols.  They are what the reference's two plug-in boundaries bind to:
+ *
+ *   (1) the onnxruntime custom-op library  (reference: src/ort_custom_ops)
+ *         CorrelationKernel::ComputeCUDA   correlation_cuda.cc:29-138  ->  vsc_correlation_f32
+ *         WarpKernel::ComputeCUDA          warp_cuda.cc:28-77          ->  vsc_warp_nchw_f32
+ *   (2) the stabilization interface        (reference: src/stabilization)
+ *         get_warp_result   flowconsistency.cuh:19-22  / .cu:301-312   ->  vsc_warp_hwc3
+ *         get_adap_comb     flowconsistency.cuh:25-36  / .cu:314-333   ->  vsc_adap_comb
+ *         get_consist_wt    flowconsistency.cuh:38-43  / .cu:335-348   ->  vsc_consist_wt
+ *         get_bilinear      flowconsistency.cuh:15-17  / .cu:288-299   ->  vsc_bilinear
+ *         get_consist_out   flowconsistency.cuh:45-52  / .cu:350-374   ->  vsc_consist_solve
+ *         GPUImage::copyFromQImage  gpuimage.cpp:103-124 / gpuimage.cu:39-51,70-104  ->  vsc_rgba8_to_f32x3
+ *         GPUImage::copyToQImage    gpuimage.cpp:127-135 / gpuimage.cu:54-67,107-135 ->  vsc_f32x3_to_rgba8
+ *         VideoStabilizer::doOneStep  videostabilizer.cpp:167-265      ->  vsc_stage_a_fused + vsc_frame_solve,
+ *                                                                          or the vsc_stabilizer_* object
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats; no C++/torch/ORT types.  `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).
+ *   - every pointer named *_dev / documented "device" is device memory on the current device.
+ *   - kernels are enqueued on `stream`; the functions never synchronise, never allocate device
+ *     memory and never touch the default stream unless asked to (the reference does all three:
+ *     correlation_cuda.cu:369-370,440-441; flowconsistency.cu:285,363-365).  Scratch memory is
+ *     caller-owned (vsc_*_workspace_bytes) except inside the vsc_stabilizer object, which
+ *     allocates once at creation.
+ *   - return value: 0 (VSC_OK) or a negative VSC_E_* for argument errors, or a positive
+ *     cudaError_t from the launch.  No exceptions cross this boundary, nothing calls exit().
+ *   - images: float, interleaved HWC, data[(y*W + x)*C + c]  (gpuimage.h:15-20);
+ *     op tensors: float NCHW, contiguous.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns the
+ *     cudaError_t of the failed launch.
+ */
+#ifndef VSC_VSC_H
+#define VSC_VSC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_MSC_VER)
+#define VSC_API __declspec(dllexport)
+#else
+#define VSC_API __attribute__((visibility("default")))
+#endif
+
+#define VSC_VERSION 100 /* 0.1.0 */
+
+enum {
+    VSC_OK = 0,
+    VSC_E_INVALID = -1,   /* null pointer / non-positive size / unsupported channel count */
+    VSC_E_WORKSPACE = -2, /* workspace missing or too small */
+    VSC_E_STATE = -3,     /* stabilizer called out of order (e.g. step before 3 frames were pushed) */
+    VSC_E_ALIGN = -4      /* pointer not aligned to 4 bytes */
+};
+
+typedef void* vsc_stream_t; /* cudaStream_t */
+
+VSC_API int vsc_version(void);
+/* static string for VSC_E_* codes and cudaError_t values */
+VSC_API const char* vsc_error_string(int code);
+/* number of kernels this library has launched in this process (all entry points); the benchmark's
+ * "gpu_launches" claim is read from here */
+VSC_API uint64_t vsc_launch_count(void);
+
+/* ------------------------------------------------------------------ ORT custom ops (NCHW fp32)
+ *
+ * custom::Correlation (domain "custom", attributes legacy, max_displacement; correlation.h:19-31)
+ *   legacy == 0:  out[N, P, P, H, W],  P = 2*max_displacement+1
+ *                 out[n,ph,pw,h,w] = sum_c in1[n,c,h,w] * in2[n,c,h+ph-md,w+pw-md], outside = 0
+ *   legacy != 0:  out[N, P*P, H, W] = the same sums divided by C (correlation_cuda.cu:183-265);
+ *                 the two layouts are byte-identical, only the 1/C scale differs.
+ * in1/in2/out: device. */
+VSC_API int vsc_correlation_f32(const float* in1, const float* in2, float* out, int N, int C, int H, int W,
+    int max_displacement, int legacy, vsc_stream_t stream);
+
+/* custom::Warp: masked bilinear backward warp (warp.cc:71-134 / warp_cuda.cu:29-84).
+ * in [N,C,H,W], flow [N,2,H,W] (pixels), out [N,C,H,W]; out = 0 where the bilinear validity
+ * mask is <= 0.999. */
+VSC_API int vsc_warp_nchw_f32(const float* in, const float* flow, float* out, int N, int C, int H, int W,
+    vsc_stream_t stream);
+
+/* ------------------------------------------------------------------ stabilization (HWC fp32, 3 channels)
+ * flow_channels: 3 (model output u,v,0; videostabilizer.cpp:50-51) or 2 (.flo layout); only u,v are read. */
+VSC_API int vsc_warp_hwc3(const float* in, const float* flow, float* out, int W, int H, int flow_channels,
+    vsc_stream_t stream);
+
+/* adapCmbIn may be NULL (it is only an input of vsc_consist_wt). */
+VSC_API int vsc_adap_comb(const float* crntIn, const float* crntPr, const float* prevWarpIn, const float* prevWarpPr,
+    const float* nextWarpIn, const float* nextWarpPr, float* adapCmbIn, float* adapCmbPr, const float* lastStabWarp,
+    float alpha, int W, int H, vsc_stream_t stream);
+
+VSC_API int vsc_consist_wt(const float* adapCmbIn, const float* crntIn, float* consWt, float beta, float gamma, int W,
+    int H, vsc_stream_t stream);
+
+/* resize without half-pixel offset; writes Co channels, reads with stride Ci (Co <= Ci) */
+VSC_API int vsc_bilinear(const float* in, int Wi, int Hi, int Ci, float* out, int Wo, int Ho, int Co,
+    vsc_stream_t stream);
+
+/* get_consist_out: numIter sweeps of the screened-Poisson gradient descent on consisOut (in/out,
+ * caller-initialised).  Deterministic Jacobi ordering (the reference's in-place update is a data
+ * race, flowconsistency.cu:370).  workspace: device scratch of at least
+ * vsc_consist_solve_workspace_bytes(W,H) bytes, contents undefined on entry and exit. */
+VSC_API size_t vsc_consist_solve_workspace_bytes(int W, int H);
+VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, const float* consWt, int numIter,
+    float stepSize, float momFac, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
+    vsc_stream_t stream);
+
+/* RGBA8888 (device bytes) <-> float3.  to-float: float(u8)/255 (alpha ignored);
+ * to-u8: (uint8)floor(|v|*255) without clamp (wraps mod 256), alpha byte = 1 (gpuimage.cu:39-67). */
+VSC_API int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, int H, vsc_stream_t stream);
+VSC_API int vsc_f32x3_to_rgba8(const float* in, uint8_t* rgba_dev, int W, int H, vsc_stream_t stream);
+
+/* Fused "stage A" of doOneStep (videostabilizer.cpp:182-198): the five get_warp_result calls,
+ * get_adap_comb and get_consist_wt in ONE pass -- no warped intermediates touch HBM.
+ * Outputs adapCmbPr and consWt (and adapCmbIn if non-NULL). */
+VSC_API int vsc_stage_a_fused(const float* origPrev, const float* origCur, const float* origNext,
+    const float* procPrev, const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd,
+    const float* flowBwd, int flow_channels, float alpha, float beta, float gamma, float* adapCmbIn, float* adapCmbPr,
+    float* consWt, int W, int H, vsc_stream_t stream);
+
+/* hyperParams of the reference, same field order (videostabilizer.h:38-46) */
+typedef struct vsc_hyper_params {
+    float alpha;
+    float beta;
+    float gamma;
+    int pyramidLevels;
+    int numIter;
+    float stepSize;
+    float momFac;
+} vsc_hyper_params;
+/* defaults of VideoStabilizer::initHyperParams (videostabilizer.cpp:104-112) */
+VSC_API void vsc_hyper_params_default(vsc_hyper_params* p);
+
+/* The pyramid + solver part of doOneStep (videostabilizer.cpp:200-228): pyramid of
+ * p->pyramidLevels levels (sizes halved with integer division), coarse-to-fine solve with
+ * numIter/(j+1) sweeps at level j, result in consisOut (full resolution, need not be initialised).
+ * workspace >= vsc_frame_solve_workspace_bytes(W,H,levels). */
+VSC_API size_t vsc_frame_solve_workspace_bytes(int W, int H, int pyramidLevels);
+VSC_API int vsc_frame_solve(const float* procCur, const float* adapCmbPr, const float* consWt,
+    const vsc_hyper_params* p, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
+    vsc_stream_t stream);
+
+/* ------------------------------------------------------------------ per-stream pipeline object
+ * Mirror of VideoStabilizer's recurrence (videostabilizer.cpp:136-153,167-265) for ONE video
+ * stream on the current device: a sliding window [prev,cur,next] of original+processed frames,
+ * the fp32 lastStabilizedFrame state, all persistent device buffers, a compute stream and a copy
+ * stream with pinned staging (frames are uploaded asynchronously while the previous frame is
+ * being solved).  Independent streams = independent objects, one per GPU for multi-GPU. */
+typedef struct vsc_stabilizer vsc_stabilizer;
+
+VSC_API int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flow_channels);
+VSC_API void vsc_stabilizer_destroy(vsc_stabilizer* s);
+/* live pointer, like VideoStabilizer::getHyperParams(); snapshotted once per step (:192) */
+VSC_API vsc_hyper_params* vsc_stabilizer_hyper_params(vsc_stabilizer* s);
+/* loadFrame(): append one (original, processed) RGBA8888 frame pair from HOST memory to the
+ * window (upload + u8->f32 on the copy stream).  The third push after creation/reset also
+ * initialises lastStabilizedFrame from that processed frame (preloadProcessedFrames :152).
+ * Host buffers may be pageable (staged through internal pinned buffers) or pinned
+ * (vsc_host_alloc / cudaHostRegister: copied directly); they may be reused once the call returns
+ * if pageable, or after the next vsc_stabilizer_step/sync if pinned. */
+VSC_API int vsc_stabilizer_push_frame(vsc_stabilizer* s, const uint8_t* orig_rgba_host,
+    const uint8_t* proc_rgba_host);
+/* doOneStep(): stabilise window[1] with flow cur->next (flowFwd) and the flow the reference uses
+ * as cur->prev (flowBwd), both DEVICE HWC images of flow_channels channels at frame resolution.
+ * Writes the RGBA8888 result to out_rgba_host (if non-NULL; valid after vsc_stabilizer_sync),
+ * updates lastStabilizedFrame and pops the window front.  Requires 3 frames in the window. */
+VSC_API int vsc_stabilizer_step(vsc_stabilizer* s, const float* flowFwd_dev, const float* flowBwd_dev,
+    uint8_t* out_rgba_host);
+/* same, flows given at a lower resolution (FLOWDOWNSCALE, flowmodel.cpp:156-165): upsampled with
+ * vsc_bilinear semantics (values not rescaled, as the reference) inside the step */
+VSC_API int vsc_stabilizer_step_lowres_flow(vsc_stabilizer* s, const float* flowFwd_dev, const float* flowBwd_dev,
+    int flowW, int flowH, uint8_t* out_rgba_host);
+VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
+/* device pointer to the fp32 result of the last step (W*H*3 floats), for tests */
+VSC_API const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s);
+/* enqueue a device-to-device copy of that result into dst_dev on the compute stream */
+VSC_API int vsc_stabilizer_copy_last_output(vsc_stabilizer* s, float* dst_dev);
+VSC_API vsc_stream_t vsc_stabilizer_compute_stream(vsc_stabilizer* s);
+/* clears the window and the recurrence (seek) */
+VSC_API int vsc_stabilizer_reset(vsc_stabilizer* s);
+
+/* pinned host memory for frame buffers (cudaHostAlloc / cudaFreeHost) */
+VSC_API int vsc_host_alloc(void** p, size_t bytes);
+VSC_API int vsc_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSC_VSC_H */

@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE -- not product code.
+//
+// Driver that runs the reference's OWN CPU custom-op kernels
+// (/root/reference/src/ort_custom_ops/src/opticalflow/{correlation,warp}.cc, compiled
+// unmodified against the stand-in ORT headers in oracle/shim/ort) on plain host
+// buffers.  It goes through CorrelationKernel::Compute / WarpKernel::Compute
+// (correlation.h:33-49, warp.h:18-31), i.e. through the same shape logic and
+// attribute handling ORT would exercise.  Built by oracle/Makefile into
+// oracle/_ref/libvsc_ref_cpu.so; used by tests/ (golden-vector generation, oracle
+// pinning) and by bench.py's cpu_baseline / --impl reference legs only.
+#include <ort_custom_ops/opticalflow/correlation.h>
+#include <ort_custom_ops/opticalflow/warp.h>
+
+#include <cstdio>
+#include <cstring>
+#include <exception>
+
+namespace {
+
+struct OutSlot {
+    void* ptr;
+    size_t bytes;
+};
+
+void* take_output(void* user, size_t /*index*/, size_t bytes)
+{
+    OutSlot* s = static_cast<OutSlot*>(user);
+    if (bytes > s->bytes)
+        throw std::runtime_error("ref driver: output buffer too small");
+    s->bytes = bytes;
+    return s->ptr;
+}
+
+const OrtApi g_api{};
+
+}  // namespace
+
+extern "C" {
+
+// returns 0 on success; 1 = exception (message printed); out_rank/out_dims report what the op asked ORT for
+int vsc_ref_cpu_correlation(const float* in1, const float* in2, float* out, size_t out_bytes, int64_t N, int64_t C,
+    int64_t H, int64_t W, int64_t max_displacement, int64_t legacy, int64_t* out_dims, int* out_rank)
+{
+    try {
+        OrtKernelInfo info;
+        info.legacy = legacy;
+        info.max_displacement = max_displacement;
+        CorrelationKernel k(g_api, &info, "CPUExecutionProvider");
+        OrtKernelContext ctx;
+        OutSlot slot{out, out_bytes};
+        ctx.alloc_output = take_output;
+        ctx.alloc_user = &slot;
+        ctx.inputs.resize(2);
+        ctx.inputs[0].shape = {N, C, H, W};
+        ctx.inputs[0].data = const_cast<float*>(in1);
+        ctx.inputs[1].shape = {N, C, H, W};
+        ctx.inputs[1].data = const_cast<float*>(in2);
+        k.Compute(&ctx);
+        if (out_rank)
+            *out_rank = static_cast<int>(ctx.outputs[0].shape.size());
+        if (out_dims)
+            for (size_t i = 0; i < ctx.outputs[0].shape.size(); ++i)
+                out_dims[i] = ctx.outputs[0].shape[i];
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_ref_cpu_correlation: %s\n", e.what());
+        return 1;
+    }
+}
+
+int vsc_ref_cpu_warp(const float* in, const float* flow, float* out, size_t out_bytes, int64_t N, int64_t C, int64_t H,
+    int64_t W)
+{
+    try {
+        OrtKernelInfo info;
+        WarpKernel k(g_api, &info, "CPUExecutionProvider");
+        OrtKernelContext ctx;
+        OutSlot slot{out, out_bytes};
+        ctx.alloc_output = take_output;
+        ctx.alloc_user = &slot;
+        ctx.inputs.resize(2);
+        ctx.inputs[0].shape = {N, C, H, W};
+        ctx.inputs[0].data = const_cast<float*>(in);
+        ctx.inputs[1].shape = {N, 2, H, W};
+        ctx.inputs[1].data = const_cast<float*>(flow);
+        k.Compute(&ctx);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_ref_cpu_warp: %s\n", e.what());
+        return 1;
+    }
+}
+
+// missing-attribute behaviour of the reference ctor (correlation.h:19-31): returns 1 if it threw
+int vsc_ref_cpu_correlation_ctor_throws(int has_legacy, int has_max_displacement)
+{
+    try {
+        OrtKernelInfo info;
+        info.has_legacy = has_legacy != 0;
+        info.has_max_displacement = has_max_displacement != 0;
+        CorrelationKernel k(g_api, &info, "CPUExecutionProvider");
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+}

@@ -1,0 +1,173 @@
+"""GPU parity of the two ORT custom ops (through the C ABI) against the oracle and the reference fixtures.
+
+Tolerance (north_star): <= 1e-4 relative for Correlation / Warp fp32 tensors, measured norm-wise as
+max|d| / max|ref| (BASELINE.md "Parity gates").  Observed values are ~1e-7 (fp32 rounding: FMA vs mul+add).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ops_golden.npz")
+TOL = 1e-4
+
+
+def rel(a, ref):
+    return float(np.abs(a - ref).max() / max(float(np.abs(ref).max()), 1e-30))
+
+
+def cu(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+# ---------------------------------------------------------------- Correlation
+@pytest.mark.parametrize("shape", [
+    (1, 1, 1, 1), (1, 3, 5, 7), (2, 12, 13, 21), (1, 8, 8, 32), (1, 9, 33, 65), (1, 64, 18, 30), (1, 196, 9, 15),
+    (3, 16, 40, 44), (1, 7, 72, 120),
+])
+def test_correlation_vs_oracle(V, O, dev, shape):
+    N, C, H, W = shape
+    a, b = synth.features(N, C, H, W, 1), synth.features(N, C, H, W, 2)
+    got = V.correlation(cu(a, dev), cu(b, dev)).cpu().numpy()
+    ref = O.correlation(a, b)
+    assert got.shape == (N, 9, 9, H, W)
+    assert rel(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("C", [16, 12, 96])
+def test_correlation_legacy_layout(V, O, dev, C):
+    a, b = synth.features(2, C, 14, 20, 3), synth.features(2, C, 14, 20, 4)
+    got = V.correlation(cu(a, dev), cu(b, dev), legacy=True).cpu().numpy()
+    ref = O.correlation(a, b, legacy=True)
+    assert got.shape == (2, 81, 14, 20)
+    assert rel(got, ref) <= TOL
+    # same bytes as the new layout up to the 1/C scale
+    new = V.correlation(cu(a, dev), cu(b, dev)).cpu().numpy().reshape(2, 81, 14, 20)
+    assert rel(got, new / np.float32(C)) <= 1e-6
+
+
+@pytest.mark.parametrize("md", [0, 1, 2, 6])
+def test_correlation_other_displacements(V, O, dev, md):
+    a, b = synth.features(1, 10, 11, 17, 5), synth.features(1, 10, 11, 17, 6)
+    got = V.correlation(cu(a, dev), cu(b, dev), max_displacement=md).cpu().numpy()
+    ref = O.correlation(a, b, max_displacement=md)
+    assert got.shape == ref.shape
+    assert rel(got, ref) <= TOL
+
+
+def test_correlation_golden(V, dev):
+    g = np.load(GOLD)
+    for name in ("corr_ragged", "corr_level", "corr_testpy"):
+        got = V.correlation(cu(g[name + "_in1"], dev), cu(g[name + "_in2"], dev)).cpu().numpy()
+        assert rel(got, g[name + "_out"]) <= TOL, name
+
+
+def test_correlation_reference_test_shape(V, O, dev):
+    """model-conversion/test.py:47-48: rand(4,64,128,128)*10, run twice on the same stream."""
+    rng = np.random.default_rng(0)
+    a = rng.random((4, 64, 128, 128), dtype=np.float32) * 10
+    b = rng.random((4, 64, 128, 128), dtype=np.float32) * 10
+    ta, tb = cu(a, dev), cu(b, dev)
+    got1 = V.correlation(ta, tb)
+    got2 = V.correlation(ta, tb)
+    assert torch.equal(got1, got2)
+    # oracle on one batch element (seconds on the host)
+    ref = O.correlation(a[:1], b[:1])
+    assert rel(got1[:1].cpu().numpy(), ref) <= TOL
+
+
+def test_correlation_full_size_properties(V, dev):
+    """dense-4K level 2 (32,544,960): properties that need no CPU reference."""
+    C, H, W = 32, 544, 960
+    g = torch.Generator(device=dev).manual_seed(3)
+    a = torch.randn((1, C, H, W), device=dev, generator=g)
+    b = torch.randn((1, C, H, W), device=dev, generator=g)
+    out = V.correlation(a, b)
+    # centre displacement == channel dot product
+    dot = (a * b).sum(1)
+    assert float((out[:, 4, 4] - dot).abs().max() / dot.abs().max()) <= 1e-5
+    # displacement (ph,pw) == dot product with the shifted second input, zero outside
+    for ph, pw in ((0, 0), (8, 8), (2, 7), (6, 1)):
+        dy, dx = ph - 4, pw - 4
+        sh = torch.zeros_like(b)
+        ys, ye = max(0, -dy), min(H, H - dy)
+        xs, xe = max(0, -dx), min(W, W - dx)
+        sh[:, :, ys:ye, xs:xe] = b[:, :, ys + dy:ye + dy, xs + dx:xe + dx]
+        ref = (a * sh).sum(1)
+        assert float((out[:, ph, pw] - ref).abs().max() / ref.abs().max()) <= 1e-5
+    # linearity in the first argument
+    out2 = V.correlation(2.0 * a, b)
+    assert torch.equal(out2, 2.0 * out)
+    # symmetry: corr(a,b)[ph,pw](h,w) == corr(b,a)[8-ph,8-pw](h+dy,w+dx)
+    outT = V.correlation(b, a)
+    assert float((out[0, 6, 3, 0:H - 2, 1:W] - outT[0, 2, 5, 2:H, 0:W - 1]).abs().max()) <= 1e-3
+
+
+# ---------------------------------------------------------------- Warp
+@pytest.mark.parametrize("shape,sigma", [
+    ((1, 1, 2, 2), 1.0), ((2, 5, 13, 21), 5.0), ((1, 8, 16, 12), 0.5), ((1, 64, 18, 30), 2.0), ((2, 3, 33, 64), 3.0),
+    ((1, 4, 7, 100), 40.0), ((1, 96, 36, 60), 2.0),
+])
+def test_warp_vs_oracle(V, O, dev, shape, sigma):
+    N, C, H, W = shape
+    x = synth.features(N, C, H, W, 7)
+    f = synth.op_flow(N, H, W, 8, sigma)
+    got = V.warp(cu(x, dev), cu(f, dev)).cpu().numpy()
+    ref = O.warp_nchw(x, f)
+    assert rel(got, ref) <= TOL
+    # the validity decision (mask > 0.999) is reproduced exactly: same zero pattern
+    assert np.array_equal(got == 0, ref == 0)
+
+
+def test_warp_golden(V, dev):
+    g = np.load(GOLD)
+    for name in ("warp_big", "warp_testpy", "warp_edge"):
+        got = V.warp(cu(g[name + "_in"], dev), cu(g[name + "_flow"], dev)).cpu().numpy()
+        ref = g[name + "_out"]
+        assert rel(got, ref) <= TOL, name
+        assert np.array_equal(got == 0, ref == 0), name
+
+
+def test_warp_nonfinite(V, O, dev):
+    """NaN / inf flow and non-finite input values outside the sampled taps must behave like the reference."""
+    x = synth.features(1, 2, 6, 8, 9)
+    f = synth.op_flow(1, 6, 8, 10, 1.0)
+    f[0, 0, 2, 3] = np.nan
+    f[0, 1, 4, 1] = np.inf
+    f[0, 0, 0, 0] = -1e30
+    got = V.warp(cu(x, dev), cu(f, dev)).cpu().numpy()
+    ref = O.warp_nchw(x, f)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert rel(np.nan_to_num(got), np.nan_to_num(ref)) <= TOL
+
+
+def test_warp_identity_and_shift(V, dev):
+    """size-independent properties at the dense-4K level-2 shape: zero flow is the identity; an integer shift
+    is a translation with zeros where the source leaves the image."""
+    C, H, W = 32, 544, 960
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn((1, C, H, W), device=dev, generator=g)
+    z = torch.zeros((1, 2, H, W), device=dev)
+    assert torch.equal(V.warp(x, z), x)
+    f = z.clone()
+    f[:, 0] = 3.0
+    f[:, 1] = -2.0
+    out = V.warp(x, f)
+    ref = torch.zeros_like(x)
+    ref[:, :, 2:H, 0:W - 3] = x[:, :, 0:H - 2, 3:W]
+    assert torch.equal(out, ref)
+
+
+def test_ops_reject_bad_arguments(V, dev):
+    a = torch.zeros((1, 2, 4, 4), device=dev)
+    with pytest.raises(V.VscError):
+        V.correlation(a, torch.zeros((1, 2, 4, 5), device=dev))
+    with pytest.raises(V.VscError):
+        V.warp(a, torch.zeros((1, 3, 4, 4), device=dev))
+    with pytest.raises(V.VscError):
+        V.warp(a.cpu(), torch.zeros((1, 2, 4, 4)))  # no CPU fallback
+    assert V.lib().vsc_correlation_f32(None, None, None, 1, 1, 1, 1, 4, 0, None) == -1

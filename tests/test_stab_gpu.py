@@ -1,0 +1,332 @@
+"""GPU parity of the stabilization path (through the C ABI) against the oracle and against fixtures produced by
+the reference's own CUDA kernels on a B200 (tests/golden/stab_golden.npz).
+
+Gates
+  * warp / bilinear / u8 conversions: bit-exact against the oracle (same fp32 expression order, no FMA);
+  * adap_comb / consist_wt: <= 2e-6 absolute (CUDA expf vs glibc expf, both <= 2 ulp) away from the 0.001 / clamp
+    thresholds; at a threshold one value may flip (reference behaviour) -- bounded outlier budget;
+  * solver fp32 image: <= 2e-5 absolute against the Jacobi oracle (different but equivalent fp32 evaluation order);
+  * 8-bit stabilized frames: <= 1/255 max-abs (north_star) against oracle AND against the reference GPU fixtures.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "stab_golden.npz")
+
+
+def cu(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def near(a, b, tol, budget=0.0):
+    """max|a-b| <= tol except for at most `budget` fraction of elements."""
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    bad = (d > tol).mean()
+    return bad <= budget, f"max {d.max():.3e}, frac>{tol:g}: {bad:.2e}"
+
+
+SIZES = [(64, 48), (45, 37), (2, 2), (3, 5), (130, 7), (32, 33)]
+
+
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("fc", [3, 2])
+def test_warp_result_exact(V, O, dev, W, H, fc):
+    img = synth.f32_images(W, H, 1, 1)[0]
+    ff, _ = synth.flows(W, H, fc)
+    ff[..., :2] *= 3.0
+    got = V.get_warp_result(cu(img, dev), cu(ff, dev)).cpu().numpy()
+    assert np.array_equal(got, O.warp_hwc3(img, ff))
+
+
+@pytest.mark.parametrize("Wi,Hi,Wo,Ho,C", [(64, 48, 32, 24, 3), (45, 37, 22, 18, 3), (22, 18, 45, 37, 3),
+                                            (960, 540, 1920, 1080, 3), (31, 17, 64, 40, 2), (5, 5, 5, 5, 3),
+                                            (7, 3, 1, 1, 3)])
+def test_bilinear_exact(V, O, dev, Wi, Hi, Wo, Ho, C):
+    rng = np.random.default_rng(Wi * 7 + Ho)
+    img = rng.random((Hi, Wi, C), dtype=np.float32)
+    got = V.get_bilinear(cu(img, dev), Wo, Ho).cpu().numpy()
+    assert np.array_equal(got, O.bilinear(img, Wo, Ho))
+
+
+def test_u8_conversions_exact(V, O, dev):
+    rng = np.random.default_rng(4)
+    rgba = rng.integers(0, 256, (37, 45, 4), dtype=np.uint8)
+    rgba[0, :, 0] = np.arange(45) * 5  # cover many byte values deterministically
+    f = V.image_to_gpu(cu(rgba, dev)).cpu().numpy()
+    assert np.array_equal(f, O.rgba8_to_f32x3(rgba))
+    vals = np.concatenate([np.linspace(-1.5, 2.5, 37 * 45 * 3 - 6, dtype=np.float32),
+                           np.array([np.nan, np.inf, -np.inf, 1.0, 255.5 / 255, 1e20], np.float32)]).reshape(37, 45, 3)
+    got = V.gpu_to_image(cu(vals, dev)).cpu().numpy()
+    assert np.array_equal(got, O.f32x3_to_rgba8(vals))
+    assert (got[..., 3] == 1).all()  # the reference writes alpha = 1 (gpuimage.cu:66)
+
+
+@pytest.mark.parametrize("W,H", SIZES[:2] + [(33, 9)])
+def test_adap_comb_and_consist_wt(V, O, dev, W, H):
+    ims = synth.f32_images(W, H, 2, 7)
+    base = ims[0]
+    rng = np.random.default_rng(3)
+    # values close to each other so that the exponentials are not all clamped to 0
+    a = [np.clip(base + rng.normal(0, s, base.shape), 0, 1).astype(np.float32)
+         for s in (0, 0.02, 0.01, 0.03, 0.015, 0.03, 0.02)]
+    for alpha in (6800.0, 300.0):
+        gi, gp = V.get_adap_comb(*[cu(x, dev) for x in a], alpha)
+        ri, rp = O.adap_comb(*a, alpha)
+        ok, msg = near(gi.cpu().numpy(), ri, 2e-6, 1e-3)
+        assert ok, msg
+        ok, msg = near(gp.cpu().numpy(), rp, 2e-6, 1e-3)
+        assert ok, msg
+        for beta, gamma in ((6800.0, 2.0), (500.0, 10.0), (6800.0, 0.1)):
+            gw = V.get_consist_wt(cu(ri, dev), cu(a[0], dev), beta, gamma).cpu().numpy()
+            ok, msg = near(gw, O.consist_wt(ri, a[0], beta, gamma), 2e-6 * max(gamma, 1), 1e-3)
+            assert ok, msg
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (45, 37), (2, 2), (3, 3), (4, 9), (130, 6)])
+@pytest.mark.parametrize("iters", [0, 1, 2, 7, 150])
+def test_solver_vs_jacobi_oracle(V, O, dev, W, H, iters):
+    pr, tg, wt0 = synth.f32_images(W, H, 11, 3)
+    wt = (wt0 * 2.0 * (wt0 > 0.3)).astype(np.float32)  # zero-weight regions + weights up to gamma
+    got = V.get_consist_out(cu(pr, dev), cu(tg, dev), cu(wt, dev), iters, 0.15, 0.15, cu(pr, dev).clone())
+    ref = O.consist_out(pr, tg, wt, iters, 0.15, 0.15, pr, mode=0)
+    ok, msg = near(got.cpu().numpy(), ref, 2e-5)
+    assert ok, msg
+
+
+def test_solver_is_deterministic_and_close_to_gauss_seidel(V, O, dev):
+    W, H = 96, 64
+    pr, tg, wt0 = synth.f32_images(W, H, 12, 3)
+    wt = (wt0 * 2.0 * (wt0 > 0.3)).astype(np.float32)
+    runs = [V.get_consist_out(cu(pr, dev), cu(tg, dev), cu(wt, dev), 150, 0.15, 0.15, cu(pr, dev).clone())
+            for _ in range(3)]
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    gs = O.consist_out(pr, tg, wt, 150, 0.15, 0.15, pr, mode=1)  # sequential in-place ordering of the reference code
+    d = np.abs(runs[0].cpu().numpy() - gs).max()
+    assert d <= 1.0 / 255.0, d
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (45, 37)])
+@pytest.mark.parametrize("fc", [3, 2])
+def test_stage_a_fused_equals_unfused(V, O, dev, W, H, fc):
+    o8, p8 = synth.frames(W, H, 3, seed=5)
+    of = [V.image_to_gpu(cu(x, dev)) for x in o8]
+    pf = [V.image_to_gpu(cu(x, dev)) for x in p8]
+    ff, fb = synth.flows(W, H, fc)
+    dff, dfb = cu(ff, dev), cu(fb, dev)
+    last = pf[2]
+    aI, aP, wt = V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], last, dff, dfb, 6800.0, 6800.0, 2.0,
+                                 want_adap_in=True)
+    pI, pP = V.get_warp_result(of[0], dfb), V.get_warp_result(pf[0], dfb)
+    nI, nP = V.get_warp_result(of[2], dff), V.get_warp_result(pf[2], dff)
+    lW = V.get_warp_result(last, dfb)
+    uI, uP = V.get_adap_comb(of[1], pf[1], pI, pP, nI, nP, lW, 6800.0)
+    uw = V.get_consist_wt(uI, of[1], 6800.0, 2.0)
+    assert torch.equal(aI, uI) and torch.equal(aP, uP) and torch.equal(wt, uw)
+    # and without the optional output
+    _, aP2, wt2 = V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], last, dff, dfb, 6800.0, 6800.0, 2.0)
+    assert torch.equal(aP2, aP) and torch.equal(wt2, wt)
+
+
+def _oracle_sequence(O, o8, p8, ff, fb, steps, params=None):
+    of = [O.rgba8_to_f32x3(x) for x in o8]
+    pf = [O.rgba8_to_f32x3(x) for x in p8]
+    last = pf[2]
+    outs = []
+    for t in steps:
+        co, rgba = O.do_one_step(of[t - 1], of[t], of[t + 1], pf[t - 1], pf[t], pf[t + 1], last, ff, fb, params)
+        last = co
+        outs.append((co, rgba))
+    return outs
+
+
+@pytest.mark.parametrize("W,H,fc", [(64, 48, 3), (45, 37, 3), (64, 48, 2), (50, 30, 3)])
+def test_stabilizer_sequence_vs_oracle(V, O, dev, W, H, fc):
+    """preload + 3 doOneStep calls through the pipeline object with HOST frames (pageable), vs the oracle."""
+    T = 6
+    o8, p8 = synth.frames(W, H, T, seed=77, mismatch=0.25)
+    ff, fb = synth.flows(W, H, fc)
+    ref = _oracle_sequence(O, o8, p8, ff, fb, (1, 2, 3))
+    st = V.Stabilizer(W, H, fc)
+    dff, dfb = cu(ff, dev), cu(fb, dev)
+    torch.cuda.synchronize()
+    for t in range(3):
+        st.push_frame(o8[t], p8[t])
+    for i, t in enumerate((1, 2, 3)):
+        out = np.zeros((H, W, 4), np.uint8)
+        st.step(dff, dfb, out)
+        st.push_frame(o8[t + 2], p8[t + 2])
+        got_f = st.last_output().cpu().numpy()
+        ok, msg = near(got_f, ref[i][0], 3e-5)
+        assert ok, f"step {t}: {msg}"
+        d = np.abs(out.astype(np.int32) - ref[i][1].astype(np.int32))
+        assert d.max() <= 1, f"step {t}: u8 max diff {d.max()}"
+        assert (d > 0).mean() < 0.01
+    st.close()
+
+
+def test_stabilizer_pinned_and_lowres_flow(V, O, dev):
+    """FLOWDOWNSCALE=2 path (flowmodel.cpp:156-165): low-res flow upsampled, values not rescaled; pinned host
+    buffers take the direct-copy path."""
+    W, H = 64, 48
+    o8, p8 = synth.frames(W, H, 4, seed=78)
+    ffl, fbl = synth.flows(W // 2, H // 2, 3)
+    ff, fb = O.bilinear(ffl, W, H), O.bilinear(fbl, W, H)
+    ref = _oracle_sequence(O, o8, p8, ff, fb, (1, 2), dict(numIter=20))
+    st = V.Stabilizer(W, H, 3)
+    st.hyper_params.numIter = 20
+    po = [torch.from_numpy(x).pin_memory() for x in o8]
+    pp = [torch.from_numpy(x).pin_memory() for x in p8]
+    for t in range(3):
+        st.push_frame(po[t], pp[t])
+    outs = [V.pinned_empty((H, W, 4)) for _ in range(2)]
+    st.step(cu(ffl, dev), cu(fbl, dev), outs[0])
+    st.push_frame(po[3], pp[3])
+    st.step(cu(ffl, dev), cu(fbl, dev), outs[1])
+    st.sync()
+    for i in range(2):
+        d = np.abs(outs[i].numpy().astype(np.int32) - ref[i][1].astype(np.int32))
+        assert d.max() <= 1, d.max()
+    st.close()
+
+
+def test_stabilizer_state_errors(V, dev):
+    st = V.Stabilizer(16, 16, 3)
+    z = torch.zeros((16, 16, 3), device=dev)
+    f = np.zeros((16, 16, 4), np.uint8)
+    with pytest.raises(V.VscError):
+        st.step(z, z)  # fewer than 3 frames
+    for _ in range(3):
+        st.push_frame(f, f)
+    with pytest.raises(V.VscError):
+        st.push_frame(f, f)  # window full
+    st.step(z, z)
+    st.reset()
+    with pytest.raises(V.VscError):
+        st.step(z, z)
+    st.close()
+    with pytest.raises(V.VscError):
+        V.Stabilizer(16, 16, 4)
+
+
+def test_slider_sweep_vs_oracle(V, O, dev):
+    """hyper-parameters are runtime values (GUI sliders, hyperparameterwidget.cpp:112-128)."""
+    W, H = 48, 40
+    o8, p8 = synth.frames(W, H, 3, seed=80)
+    ff, fb = synth.flows(W, H, 3)
+    for numIter in (1, 25, 150, 400):
+        for gamma in (0.1, 2.0, 10.0):
+            params = dict(numIter=numIter, gamma=gamma)
+            ref = _oracle_sequence(O, o8, p8, ff, fb, (1,), params)
+            st = V.Stabilizer(W, H, 3)
+            st.hyper_params.numIter = numIter
+            st.hyper_params.gamma = gamma
+            for t in range(3):
+                st.push_frame(o8[t], p8[t])
+            out = np.zeros((H, W, 4), np.uint8)
+            st.step(cu(ff, dev), cu(fb, dev), out)
+            st.sync()
+            d = np.abs(out.astype(np.int32) - ref[0][1].astype(np.int32))
+            assert d.max() <= 1, (numIter, gamma, d.max())
+            st.close()
+
+
+def test_levels_other_than_two(V, O, dev):
+    W, H = 64, 48
+    o8, p8 = synth.frames(W, H, 3, seed=81)
+    ff, fb = synth.flows(W, H, 3)
+    for levels in (1, 3):
+        ref = _oracle_sequence(O, o8, p8, ff, fb, (1,), dict(pyramidLevels=levels, numIter=30))
+        st = V.Stabilizer(W, H, 3)
+        st.hyper_params.pyramidLevels = levels
+        st.hyper_params.numIter = 30
+        for t in range(3):
+            st.push_frame(o8[t], p8[t])
+        out = np.zeros((H, W, 4), np.uint8)
+        st.step(cu(ff, dev), cu(fb, dev), out)
+        st.sync()
+        d = np.abs(out.astype(np.int32) - ref[0][1].astype(np.int32))
+        assert d.max() <= 1, (levels, d.max())
+        st.close()
+
+
+# ---------------------------------------------------------------- against the reference's own CUDA kernels
+needs_gold = pytest.mark.skipif(not os.path.exists(GOLD), reason="stab_golden.npz not generated yet")
+
+
+@needs_gold
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kernels_vs_reference_gpu_fixtures(V, dev, tag):
+    g = np.load(GOLD)
+    o8, p8 = g[f"{tag}_orig8"], g[f"{tag}_proc8"]
+    ff, fb = g[f"{tag}_flowFwd"], g[f"{tag}_flowBwd"]
+    H, W = o8.shape[1:3]
+    of = [V.image_to_gpu(cu(x, dev)) for x in o8]
+    pf = [V.image_to_gpu(cu(x, dev)) for x in p8]
+    assert np.array_equal(of[0].cpu().numpy(), g[f"{tag}_to_float0"])
+    dff, dfb = cu(ff, dev), cu(fb, dev)
+    # the reference binary contracts a*b+c into FMAs where nvcc chooses; 1-ulp differences are expected
+    ok, msg = near(V.get_warp_result(of[0], dfb).cpu().numpy(), g[f"{tag}_warp_prevIn"], 5e-7)
+    assert ok, msg
+    ok, msg = near(V.get_warp_result(pf[2], dff).cpu().numpy(), g[f"{tag}_warp_nextPr"], 5e-7)
+    assert ok, msg
+    ok, msg = near(V.get_warp_result(of[0], cu(fb[..., :2], dev)).cpu().numpy(), g[f"{tag}_warp_2ch"], 5e-7)
+    assert ok, msg
+    aI, aP, wt = V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[2], dff, dfb, 6800.0, 6800.0, 2.0,
+                                 want_adap_in=True)
+    for got, key in ((aI, "adapIn"), (aP, "adapPr")):
+        ok, msg = near(got.cpu().numpy(), g[f"{tag}_{key}"], 5e-6, 2e-3)
+        assert ok, f"{key}: {msg}"
+    ok, msg = near(wt.cpu().numpy(), g[f"{tag}_consWt"], 2e-4, 5e-3)
+    assert ok, f"consWt: {msg}"
+    down = V.get_bilinear(pf[1], W // 2, H // 2)
+    ok, msg = near(down.cpu().numpy(), g[f"{tag}_bil_down"], 5e-7)
+    assert ok, msg
+    ok, msg = near(V.get_bilinear(cu(g[f"{tag}_bil_down"], dev), W, H).cpu().numpy(), g[f"{tag}_bil_up"], 5e-7)
+    assert ok, msg
+    # solver: the reference result is scheduling dependent (in-place race); gate on the 8-bit criterion
+    gaP, gwt = cu(g[f"{tag}_adapPr"], dev), cu(g[f"{tag}_consWt"], dev)
+    for it in (1, 10, 150):
+        got = V.get_consist_out(pf[1], gaP, gwt, it, 0.15, 0.15, pf[1].clone()).cpu().numpy()
+        d = np.abs(got - g[f"{tag}_solve{it}"]).max()
+        # few sweeps make the in-place race of the reference visible: its own run-to-run spread on the B200 that
+        # produced the fixture is stored beside it (0.042 at 1 sweep, 0 at 150).  Gate: 1/255 at the default 150
+        # sweeps; 3/255 + the reference's own spread below that.
+        spread = float(g[f"{tag}_solve{it}_spread"])
+        assert d <= (1.0 / 255.0 if it == 150 else 3.0 / 255.0 + spread), (it, d, spread)
+    got8 = V.gpu_to_image(cu(g[f"{tag}_solve150"], dev)).cpu().numpy()
+    assert np.array_equal(got8, g[f"{tag}_to_char"])
+    assert np.array_equal(V.gpu_to_image(cu(g[f"{tag}_to_char_odd_in"], dev)).cpu().numpy(), g[f"{tag}_to_char_odd"])
+
+
+@needs_gold
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("pname", ["default", "slider"])
+def test_sequence_vs_reference_gpu_fixtures(V, dev, tag, pname):
+    """north_star gate: <= 1/255 max-abs on the 8-bit stabilized frames vs the reference's own implementation."""
+    g = np.load(GOLD)
+    o8, p8 = g[f"{tag}_orig8"], g[f"{tag}_proc8"]
+    H, W = o8.shape[1:3]
+    st = V.Stabilizer(W, H, 3)
+    if pname == "slider":
+        st.hyper_params.numIter = 40
+        st.hyper_params.gamma = 4.0
+        st.hyper_params.alpha = 3000.0
+    dff, dfb = cu(g[f"{tag}_flowFwd"], dev), cu(g[f"{tag}_flowBwd"], dev)
+    torch.cuda.synchronize()
+    for t in range(3):
+        st.push_frame(o8[t], p8[t])
+    for t in (1, 2, 3):
+        out = np.zeros((H, W, 4), np.uint8)
+        st.step(dff, dfb, out)
+        st.push_frame(o8[t + 2], p8[t + 2])
+        st.sync()
+        ref = g[f"{tag}_{pname}_step{t}_rgba"]
+        d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= 1, f"{tag}/{pname} step {t}: max diff {d.max()} grey levels"
+    st.close()

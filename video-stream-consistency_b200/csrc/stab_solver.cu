@@ -1,0 +1,350 @@
+// The screened-Poisson consistency solver for sm_100a -- replaces get_consist_out /
+// kernel_consist_out and the pyramid loop of doOneStep (reference:
+// src/stabilization/flowconsistency.cu:193-258,350-374; videostabilizer.cpp:200-228).
+//
+// Reference: per sweep and per value it reads crntPr (5 taps), consisOut (5 taps, IN PLACE -- the
+// buffer being written, a data race, :370), consWt, prevStabWarp and prevUpdt and writes 2 arrays
+// (84 B/pixel/sweep), 225 dependent launches per frame, two cudaMallocs per call.
+//
+// Here:
+//   * deterministic Jacobi ordering: sweep k reads only sweep k-1 (two ping-pong buffers);
+//   * everything that does not change between sweeps is folded once per solve into two
+//     coefficient images (solver_prepare_kernel):
+//         cnt  = number of neighbours the reference includes (asymmetric tests, :215-236)
+//         Lp   = sum_nb pr - cnt*pr                      (Laplacian of the processed frame)
+//         A    = -step * (cnt + w)
+//         B    =  step * (w*tgt - Lp)
+//     so that one sweep is, with S = sum of the included neighbours of `out`:
+//         u'   = step*S + (A*out + B)                    ( = step * grad_val of :245 )
+//         out' = (out + u') + mom*u                      ( :249 ; u = 0 before the first sweep == isMom 0 )
+//     i.e. 2 state images (out, u) + 2 coefficient images = 72 B/pixel/sweep unblocked, 7 flops;
+//   * 128-bit accesses over the flattened row of 3W floats (x-neighbours are +-3 floats away).
+// The sweep arithmetic uses explicit FMAs; it is mathematically the reference's update and
+// differs from it only in fp32 rounding (parity: tests/test_solver.py, tolerance stated there).
+#include "vsc_common.cuh"
+
+namespace vsc {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t b) { return (b + kAlign - 1) / kAlign * kAlign; }
+
+// one thread per value; also zeroes u and (optionally) copies out -> alt
+__global__ void __launch_bounds__(256) solver_prepare_kernel(const float* __restrict__ pr,
+    const float* __restrict__ tgt, const float* __restrict__ wt, float* __restrict__ coefA, float* __restrict__ coefB,
+    float* __restrict__ u, const float* __restrict__ copy_src, float* __restrict__ copy_dst, int W, int H, float step)
+{
+    const int L = 3 * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (i >= L)
+        return;
+    const int x = i / 3;
+    const size_t idx = static_cast<size_t>(y) * L + i;
+    const float c = __ldg(pr + idx);
+    int cnt = 0;
+    float lap = 0.0f;
+    if ((x + 1) < (W - 1)) { lap += __ldg(pr + idx + 3); cnt += 1; }
+    if ((x - 1) >= 0)      { lap += __ldg(pr + idx - 3); cnt += 1; }
+    if ((y + 1) < (H - 1)) { lap += __ldg(pr + idx + L); cnt += 1; }
+    if ((y - 1) >= 0)      { lap += __ldg(pr + idx - L); cnt += 1; }
+    lap -= static_cast<float>(cnt) * c;
+    const float w = __ldg(wt + idx);
+    coefA[idx] = -step * (static_cast<float>(cnt) + w);
+    coefB[idx] = step * (w * __ldg(tgt + idx) - lap);
+    u[idx] = 0.0f;
+    if (copy_dst)
+        copy_dst[idx] = copy_src[idx];
+}
+
+__device__ __forceinline__ void sweep_value(float o, float S, float a, float b, float uo, float step, float mom,
+    float& onew, float& unew)
+{
+    unew = __fmaf_rn(step, S, __fmaf_rn(a, o, b));
+    onew = __fmaf_rn(mom, uo, o + unew);
+}
+
+// one Jacobi sweep, 4 consecutive floats of a row per thread (requires 3W % 4 == 0, 16B-aligned images)
+__global__ void __launch_bounds__(256) solver_sweep_vec_kernel(const float* __restrict__ coefA,
+    const float* __restrict__ coefB, float* __restrict__ u, const float* __restrict__ src, float* __restrict__ dst,
+    int W, int H, float step, float mom)
+{
+    const int L = 3 * W;
+    const int L4 = L >> 2;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (j >= L4)
+        return;
+    const size_t base = static_cast<size_t>(y) * L + 4 * j;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 cur = *reinterpret_cast<const float4*>(src + base);
+    const float4 prv = j > 0 ? *reinterpret_cast<const float4*>(src + base - 4) : z;
+    const float4 nxt = j < L4 - 1 ? *reinterpret_cast<const float4*>(src + base + 4) : z;
+    const float4 up = (y - 1) >= 0 ? *reinterpret_cast<const float4*>(src + base - L) : z;
+    const float4 dn = (y + 1) < (H - 1) ? *reinterpret_cast<const float4*>(src + base + L) : z;
+    const float4 a = ldg_stream4(coefA + base);
+    const float4 b = ldg_stream4(coefB + base);
+    const float4 uo = *reinterpret_cast<const float4*>(u + base);
+
+    const int i0 = 4 * j;
+    const int rlim = 3 * (W - 2);  // right neighbour included iff i < 3(W-2)  <=>  x+1 < W-1
+    const float o[4] = {cur.x, cur.y, cur.z, cur.w};
+    const float r[4] = {cur.w, nxt.x, nxt.y, nxt.z};
+    const float l[4] = {prv.y, prv.z, prv.w, cur.x};
+    const float d[4] = {dn.x, dn.y, dn.z, dn.w};
+    const float t[4] = {up.x, up.y, up.z, up.w};
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+    const float uv[4] = {uo.x, uo.y, uo.z, uo.w};
+    float on[4], un[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        const float rr = i < rlim ? r[k] : 0.0f;
+        const float ll = i >= 3 ? l[k] : 0.0f;
+        const float S = ((rr + ll) + d[k]) + t[k];
+        sweep_value(o[k], S, av[k], bv[k], uv[k], step, mom, on[k], un[k]);
+    }
+    *reinterpret_cast<float4*>(u + base) = make_float4(un[0], un[1], un[2], un[3]);
+    *reinterpret_cast<float4*>(dst + base) = make_float4(on[0], on[1], on[2], on[3]);
+}
+
+// scalar variant for rows whose length is not a multiple of 4 floats
+__global__ void __launch_bounds__(256) solver_sweep_scalar_kernel(const float* __restrict__ coefA,
+    const float* __restrict__ coefB, float* __restrict__ u, const float* __restrict__ src, float* __restrict__ dst,
+    int W, int H, float step, float mom)
+{
+    const int L = 3 * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (i >= L)
+        return;
+    const size_t idx = static_cast<size_t>(y) * L + i;
+    const float o = src[idx];
+    const float rr = i < 3 * (W - 2) ? src[idx + 3] : 0.0f;
+    const float ll = i >= 3 ? src[idx - 3] : 0.0f;
+    const float dd = (y + 1) < (H - 1) ? src[idx + L] : 0.0f;
+    const float tt = (y - 1) >= 0 ? src[idx - L] : 0.0f;
+    const float S = ((rr + ll) + dd) + tt;
+    float on, un;
+    sweep_value(o, S, coefA[idx], coefB[idx], u[idx], step, mom, on, un);
+    u[idx] = un;
+    dst[idx] = on;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n)
+{
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = src[i];
+}
+
+struct SolveBuffers {
+    float *coefA, *coefB, *u, *alt;
+};
+
+static SolveBuffers carve(void* ws, size_t n)
+{
+    char* p = static_cast<char*>(ws);
+    const size_t s = align_up(n * sizeof(float));
+    SolveBuffers b;
+    b.coefA = reinterpret_cast<float*>(p);
+    b.coefB = reinterpret_cast<float*>(p + s);
+    b.u = reinterpret_cast<float*>(p + 2 * s);
+    b.alt = reinterpret_cast<float*>(p + 3 * s);
+    return b;
+}
+
+static int launch_prepare(const float* pr, const float* tgt, const float* wt, const SolveBuffers& b,
+    const float* copy_src, float* copy_dst, int W, int H, float step, cudaStream_t st)
+{
+    const dim3 grid(cdiv(3LL * W, 256), H);
+    solver_prepare_kernel<<<grid, 256, 0, st>>>(pr, tgt, wt, b.coefA, b.coefB, b.u, copy_src, copy_dst, W, H, step);
+    count_launch();
+    return launch_status();
+}
+
+// `iters` sweeps starting from the state in x; returns through *result the buffer holding the result
+static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, int iters, float step, float mom,
+    cudaStream_t st, float** result)
+{
+    const bool vec = (3LL * W) % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(b.coefA) && aligned16(b.coefB)
+        && aligned16(b.u);
+    float* src = x;
+    float* dst = y;
+    for (int k = 0; k < iters; ++k) {
+        if (vec) {
+            const dim3 grid(cdiv(3LL * W / 4, 128), H);
+            solver_sweep_vec_kernel<<<grid, 128, 0, st>>>(b.coefA, b.coefB, b.u, src, dst, W, H, step, mom);
+        } else {
+            const dim3 grid(cdiv(3LL * W, 256), H);
+            solver_sweep_scalar_kernel<<<grid, 256, 0, st>>>(b.coefA, b.coefB, b.u, src, dst, W, H, step, mom);
+        }
+        float* t = src;
+        src = dst;
+        dst = t;
+    }
+    count_launch(iters);
+    *result = src;
+    return launch_status();
+}
+
+}  // namespace vsc
+
+using namespace vsc;
+
+extern "C" size_t vsc_consist_solve_workspace_bytes(int W, int H)
+{
+    if (W <= 0 || H <= 0)
+        return 0;
+    return 4 * align_up(static_cast<size_t>(W) * H * 3 * sizeof(float));
+}
+
+extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, const float* consWt, int numIter,
+    float stepSize, float momFac, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
+    vsc_stream_t stream)
+{
+    if (!crntPr || !prevStabWarp || !consWt || !consisOut || W <= 0 || H <= 0 || H > 65535 || numIter < 0)
+        return VSC_E_INVALID;
+    if (numIter == 0)
+        return VSC_OK;
+    if (!workspace || workspace_bytes < vsc_consist_solve_workspace_bytes(W, H) || !aligned16(workspace))
+        return VSC_E_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const size_t n = static_cast<size_t>(W) * H * 3;
+    const SolveBuffers b = carve(workspace, n);
+    // start in the buffer that makes the last sweep land in consisOut
+    const bool odd = (numIter & 1) != 0;
+    int rc = launch_prepare(crntPr, prevStabWarp, consWt, b, odd ? consisOut : nullptr, odd ? b.alt : nullptr, W, H,
+        stepSize, st);
+    if (rc)
+        return rc;
+    float* res = nullptr;
+    rc = run_sweeps(b, odd ? b.alt : consisOut, odd ? consisOut : b.alt, W, H, numIter, stepSize, momFac, st, &res);
+    return rc;
+}
+
+extern "C" void vsc_hyper_params_default(vsc_hyper_params* p)
+{
+    if (!p)
+        return;
+    p->alpha = 6800.0f;
+    p->beta = 6800.0f;
+    p->gamma = 2.0f;
+    p->pyramidLevels = 2;
+    p->numIter = 150;
+    p->stepSize = 0.15f;
+    p->momFac = 0.15f;
+}
+
+namespace {
+constexpr int kMaxLevels = 8;
+struct LevelDims {
+    int w[kMaxLevels], h[kMaxLevels];
+    size_t n[kMaxLevels];
+};
+LevelDims level_dims(int W, int H, int levels)
+{
+    LevelDims d{};
+    d.w[0] = W;
+    d.h[0] = H;
+    for (int j = 1; j < levels; ++j) {
+        d.w[j] = d.w[j - 1] / 2;  // videostabilizer.cpp:126-127
+        d.h[j] = d.h[j - 1] / 2;
+    }
+    for (int j = 0; j < levels; ++j)
+        d.n[j] = static_cast<size_t>(d.w[j]) * d.h[j] * 3;
+    return d;
+}
+}  // namespace
+
+extern "C" size_t vsc_frame_solve_workspace_bytes(int W, int H, int pyramidLevels)
+{
+    if (W <= 0 || H <= 0 || pyramidLevels < 1 || pyramidLevels > kMaxLevels)
+        return 0;
+    const LevelDims d = level_dims(W, H, pyramidLevels);
+    size_t total = 4 * align_up(d.n[0] * sizeof(float));  // level 0: A, B, u, alt
+    for (int j = 1; j < pyramidLevels; ++j)
+        total += 8 * align_up((d.n[j] ? d.n[j] : 1) * sizeof(float));  // pr, tgt, wt, out + A, B, u, alt
+    return total;
+}
+
+extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, const float* consWt,
+    const vsc_hyper_params* p, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
+    vsc_stream_t stream)
+{
+    if (!procCur || !adapCmbPr || !consWt || !p || !consisOut || W <= 0 || H <= 0 || H > 65535)
+        return VSC_E_INVALID;
+    const int levels = p->pyramidLevels;
+    if (levels < 1 || levels > kMaxLevels || p->numIter < 0)
+        return VSC_E_INVALID;
+    if (!workspace || workspace_bytes < vsc_frame_solve_workspace_bytes(W, H, levels) || !aligned16(workspace))
+        return VSC_E_WORKSPACE;
+    const LevelDims d = level_dims(W, H, levels);
+    if (d.w[levels - 1] < 1 || d.h[levels - 1] < 1)
+        return VSC_E_INVALID;
+    cudaStream_t st = as_stream(stream);
+
+    // carve the workspace
+    char* ws = static_cast<char*>(workspace);
+    SolveBuffers sb[kMaxLevels];
+    const float* pr[kMaxLevels];
+    const float* tg[kMaxLevels];
+    const float* wt[kMaxLevels];
+    float* out[kMaxLevels];
+    sb[0] = carve(ws, d.n[0]);
+    ws += 4 * align_up(d.n[0] * sizeof(float));
+    pr[0] = procCur;
+    tg[0] = adapCmbPr;
+    wt[0] = consWt;
+    out[0] = nullptr;  // chosen below
+    for (int j = 1; j < levels; ++j) {
+        const size_t s = align_up(d.n[j] * sizeof(float));
+        float* q = reinterpret_cast<float*>(ws);
+        pr[j] = q;
+        tg[j] = reinterpret_cast<float*>(ws + s);
+        wt[j] = reinterpret_cast<float*>(ws + 2 * s);
+        out[j] = reinterpret_cast<float*>(ws + 3 * s);
+        sb[j] = carve(ws + 4 * s, d.n[j]);
+        ws += 8 * s;
+    }
+
+    int rc;
+    // pyramid down (videostabilizer.cpp:210-216).  pyrConsisOut[0] is a copy of the processed frame (:209),
+    // so its downsampled version equals pyrPr[j] -- computed once and copied.
+    for (int j = 1; j < levels; ++j) {
+        rc = vsc_bilinear(pr[j - 1], d.w[j - 1], d.h[j - 1], 3, const_cast<float*>(pr[j]), d.w[j], d.h[j], 3, stream);
+        if (rc) return rc;
+        rc = vsc_bilinear(tg[j - 1], d.w[j - 1], d.h[j - 1], 3, const_cast<float*>(tg[j]), d.w[j], d.h[j], 3, stream);
+        if (rc) return rc;
+        rc = vsc_bilinear(wt[j - 1], d.w[j - 1], d.h[j - 1], 3, const_cast<float*>(wt[j]), d.w[j], d.h[j], 3, stream);
+        if (rc) return rc;
+    }
+
+    // coarse to fine (:219-227)
+    float* coarse_result = nullptr;
+    for (int j = levels - 1; j >= 0; --j) {
+        const int iters = p->numIter / (j + 1);
+        const bool odd = (iters & 1) != 0;
+        // x = buffer holding the initial state, y = the other one; the result lands in `final`
+        float* final_buf = (j == 0) ? consisOut : out[j];
+        float* x = odd ? sb[j].alt : final_buf;
+        float* y = odd ? final_buf : sb[j].alt;
+        // initial state: coarsest level = downsampled processed frame (== pr[j]); else upsampled coarser result
+        const float* copy_src = nullptr;
+        float* copy_dst = nullptr;
+        if (j == levels - 1) {
+            copy_src = pr[j];
+            copy_dst = x;
+        } else {
+            rc = vsc_bilinear(coarse_result, d.w[j + 1], d.h[j + 1], 3, x, d.w[j], d.h[j], 3, stream);
+            if (rc) return rc;
+        }
+        rc = launch_prepare(pr[j], tg[j], wt[j], sb[j], copy_src, copy_dst, d.w[j], d.h[j], p->stepSize, st);
+        if (rc) return rc;
+        float* res = nullptr;
+        rc = run_sweeps(sb[j], x, y, d.w[j], d.h[j], iters, p->stepSize, p->momFac, st, &res);
+        if (rc) return rc;
+        coarse_result = res;  // == final_buf (also when iters == 0: x == final_buf since 0 is even)
+    }
+    return VSC_OK;
+}

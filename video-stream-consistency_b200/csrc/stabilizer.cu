@@ -1,0 +1,387 @@
+// vsc_stabilizer: the per-stream pipeline object (include/vsc/vsc.h), the native counterpart of
+// VideoStabilizer's per-frame recurrence (reference: src/stabilization/videostabilizer.cpp:46-153,
+// 167-265; GPUImage::copyFromQImage / copyToQImage, gpuimage.cpp:103-135).
+//
+// What the reference does per frame and what this object does instead:
+//   * 13 member GPUImages + 8 pyramid images, plus per-call cudaMalloc/cudaFree in imageToGPU,
+//     copyToQImage and get_consist_out          -> every buffer allocated once at creation;
+//   * blocking pageable cudaMemcpy H2D per frame -> pinned staging + cudaMemcpyAsync on a copy
+//     stream; the upload and u8->f32 conversion of frame t+2 overlap the solve of frame t
+//     (4 window slots: prev, cur, next + the one being filled), ordered by events only;
+//   * 8 full-image D2D copies (flowFwd/Bwd, pyramid level 0, consisOut, lastStabilizedFrame)
+//                                                -> pointer swaps, no copies;
+//   * 240 launches each followed by cudaDeviceSynchronize -> fused stage A + solver sweeps
+//     enqueued on one compute stream, no host synchronisation inside a step;
+//   * blocking D2H of the 8-bit result           -> async D2H on a third stream into pinned memory
+//     (double buffered), overlapping the next frame.
+// One object serves one video stream on the device that was current at creation; the recurrence
+// makes frames of a stream strictly sequential, so multi-GPU = one object per GPU (no collective).
+#include "vsc_common.cuh"
+
+#include <cstring>
+#include <new>
+
+namespace {
+
+constexpr int kSlots = 4;
+
+struct Pending {
+    const uint8_t* src = nullptr;  // pinned result
+    uint8_t* dst = nullptr;        // caller's pageable buffer
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct vsc_stabilizer {
+    int W = 0, H = 0, flowC = 3, device = 0;
+    size_t P = 0, n = 0;
+    vsc_hyper_params hp{};
+    cudaStream_t compute = nullptr, copy = nullptr, d2h = nullptr;
+
+    // window ring
+    float* orig[kSlots] = {};
+    float* proc[kSlots] = {};
+    uint8_t* stage_dev[kSlots][2] = {};
+    uint8_t* stage_pin[kSlots][2] = {};
+    cudaEvent_t slot_ready[kSlots] = {};   // copy stream: upload + conversion of the slot finished
+    cudaEvent_t slot_h2d[kSlots] = {};     // copy stream: H2D from the slot's pinned staging finished
+    cudaEvent_t slot_released[kSlots] = {};  // compute stream: last step reading the slot finished
+    bool slot_used[kSlots] = {};
+    int head = 0, count = 0;
+    long long pushed = 0;
+
+    float *lastStab = nullptr, *consisOut = nullptr, *adapCmbPr = nullptr, *consWt = nullptr;
+    float* flowUp[2] = {};
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    int ws_levels = 0;
+
+    uint8_t* out_dev[2] = {};
+    uint8_t* out_pin[2] = {};
+    cudaEvent_t out_conv[2] = {};  // compute stream: f32->u8 written
+    cudaEvent_t out_done[2] = {};  // d2h stream: D2H finished
+    bool out_used[2] = {};
+    Pending pending[2];
+    int out_idx = 0;
+};
+
+namespace {
+
+using namespace vsc;
+
+int cu(cudaError_t e) { return e == cudaSuccess ? VSC_OK : static_cast<int>(e); }
+
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+void flush_pending(vsc_stabilizer* s, int k)
+{
+    Pending& pd = s->pending[k];
+    if (pd.dst) {
+        cudaEventSynchronize(s->out_done[k]);
+        std::memcpy(pd.dst, pd.src, pd.bytes);
+        pd = Pending{};
+    }
+}
+
+int ensure_workspace(vsc_stabilizer* s, int levels)
+{
+    if (levels == s->ws_levels)
+        return VSC_OK;
+    const size_t need = vsc_frame_solve_workspace_bytes(s->W, s->H, levels);
+    if (need == 0)
+        return VSC_E_INVALID;
+    if (need > s->ws_bytes) {
+        // pyramidLevels is fixed at 2 in the reference (videostabilizer.cpp:109); a change of the level count is
+        // the one case where the object re-allocates (outside any timed loop)
+        cudaStreamSynchronize(s->compute);
+        if (s->ws)
+            cudaFree(s->ws);
+        s->ws = nullptr;
+        s->ws_bytes = 0;
+        const int rc = cu(cudaMalloc(&s->ws, need));
+        if (rc)
+            return rc;
+        s->ws_bytes = need;
+    }
+    s->ws_levels = levels;
+    return VSC_OK;
+}
+
+int do_step(vsc_stabilizer* s, const float* flowFwd, const float* flowBwd, uint8_t* out_host)
+{
+    if (s->count != 3)
+        return VSC_E_STATE;
+    const vsc_hyper_params c = s->hp;  // snapshot once per frame (videostabilizer.cpp:192)
+    int rc = ensure_workspace(s, c.pyramidLevels);
+    if (rc)
+        return rc;
+    const int s0 = s->head, s1 = (s->head + 1) % kSlots, s2 = (s->head + 2) % kSlots;
+    for (int k : {s0, s1, s2})
+        if ((rc = cu(cudaStreamWaitEvent(s->compute, s->slot_ready[k], 0))))
+            return rc;
+
+    rc = vsc_stage_a_fused(s->orig[s0], s->orig[s1], s->orig[s2], s->proc[s0], s->proc[s1], s->proc[s2], s->lastStab,
+        flowFwd, flowBwd, s->flowC, c.alpha, c.beta, c.gamma, nullptr, s->adapCmbPr, s->consWt, s->W, s->H,
+        s->compute);
+    if (rc)
+        return rc;
+    rc = vsc_frame_solve(s->proc[s1], s->adapCmbPr, s->consWt, &c, s->consisOut, s->W, s->H, s->ws, s->ws_bytes,
+        s->compute);
+    if (rc)
+        return rc;
+
+    if (out_host) {
+        const int k = s->out_idx;
+        s->out_idx ^= 1;
+        flush_pending(s, k);
+        if (s->out_used[k] && (rc = cu(cudaStreamWaitEvent(s->compute, s->out_done[k], 0))))
+            return rc;
+        rc = vsc_f32x3_to_rgba8(s->consisOut, s->out_dev[k], s->W, s->H, s->compute);
+        if (rc)
+            return rc;
+        cudaEventRecord(s->out_conv[k], s->compute);
+        cudaStreamWaitEvent(s->d2h, s->out_conv[k], 0);
+        const size_t bytes = s->P * 4;
+        if (is_pinned(out_host)) {
+            rc = cu(cudaMemcpyAsync(out_host, s->out_dev[k], bytes, cudaMemcpyDeviceToHost, s->d2h));
+        } else {
+            rc = cu(cudaMemcpyAsync(s->out_pin[k], s->out_dev[k], bytes, cudaMemcpyDeviceToHost, s->d2h));
+            s->pending[k] = Pending{s->out_pin[k], out_host, bytes};
+        }
+        if (rc)
+            return rc;
+        cudaEventRecord(s->out_done[k], s->d2h);
+        s->out_used[k] = true;
+    }
+
+    // recurrence (videostabilizer.cpp:247): lastStabilizedFrame <- consisOut, as a pointer swap
+    float* t = s->lastStab;
+    s->lastStab = s->consisOut;
+    s->consisOut = t;
+    // the three window slots were read by this step; slot s0 leaves the window (:248-250)
+    for (int k : {s0, s1, s2})
+        cudaEventRecord(s->slot_released[k], s->compute);
+    s->head = s1;
+    s->count = 2;
+    return cu(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flow_channels)
+{
+    if (!out || W < 2 || H < 2 || H > 65535 || (flow_channels != 2 && flow_channels != 3))
+        return VSC_E_INVALID;
+    *out = nullptr;
+    vsc_stabilizer* s = new (std::nothrow) vsc_stabilizer;
+    if (!s)
+        return VSC_E_INVALID;
+    s->W = W;
+    s->H = H;
+    s->flowC = flow_channels;
+    s->P = static_cast<size_t>(W) * H;
+    s->n = s->P * 3;
+    vsc_hyper_params_default(&s->hp);
+    int rc = cu(cudaGetDevice(&s->device));
+    const size_t fb = s->n * sizeof(float);
+    auto dmalloc = [&](void** p, size_t b) {
+        if (!rc)
+            rc = cu(cudaMalloc(p, b));
+    };
+    auto hmalloc = [&](void** p, size_t b) {
+        if (!rc)
+            rc = cu(cudaHostAlloc(p, b, cudaHostAllocDefault));
+    };
+    auto mkevent = [&](cudaEvent_t* e) {
+        if (!rc)
+            rc = cu(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    };
+    if (!rc) rc = cu(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
+    if (!rc) rc = cu(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
+    if (!rc) rc = cu(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < kSlots; ++k) {
+        dmalloc(reinterpret_cast<void**>(&s->orig[k]), fb);
+        dmalloc(reinterpret_cast<void**>(&s->proc[k]), fb);
+        for (int i = 0; i < 2; ++i) {
+            dmalloc(reinterpret_cast<void**>(&s->stage_dev[k][i]), s->P * 4);
+            hmalloc(reinterpret_cast<void**>(&s->stage_pin[k][i]), s->P * 4);
+        }
+        mkevent(&s->slot_ready[k]);
+        mkevent(&s->slot_h2d[k]);
+        mkevent(&s->slot_released[k]);
+    }
+    dmalloc(reinterpret_cast<void**>(&s->lastStab), fb);
+    dmalloc(reinterpret_cast<void**>(&s->consisOut), fb);
+    dmalloc(reinterpret_cast<void**>(&s->adapCmbPr), fb);
+    dmalloc(reinterpret_cast<void**>(&s->consWt), fb);
+    for (int i = 0; i < 2; ++i) {
+        dmalloc(reinterpret_cast<void**>(&s->flowUp[i]), s->P * flow_channels * sizeof(float));
+        dmalloc(reinterpret_cast<void**>(&s->out_dev[i]), s->P * 4);
+        hmalloc(reinterpret_cast<void**>(&s->out_pin[i]), s->P * 4);
+        mkevent(&s->out_conv[i]);
+        mkevent(&s->out_done[i]);
+    }
+    if (!rc)
+        rc = ensure_workspace(s, s->hp.pyramidLevels);
+    if (rc) {
+        vsc_stabilizer_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return VSC_OK;
+}
+
+extern "C" void vsc_stabilizer_destroy(vsc_stabilizer* s)
+{
+    if (!s)
+        return;
+    if (s->compute) cudaStreamSynchronize(s->compute);
+    if (s->copy) cudaStreamSynchronize(s->copy);
+    if (s->d2h) cudaStreamSynchronize(s->d2h);
+    for (int k = 0; k < kSlots; ++k) {
+        cudaFree(s->orig[k]);
+        cudaFree(s->proc[k]);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(s->stage_dev[k][i]);
+            cudaFreeHost(s->stage_pin[k][i]);
+        }
+        if (s->slot_ready[k]) cudaEventDestroy(s->slot_ready[k]);
+        if (s->slot_h2d[k]) cudaEventDestroy(s->slot_h2d[k]);
+        if (s->slot_released[k]) cudaEventDestroy(s->slot_released[k]);
+    }
+    cudaFree(s->lastStab);
+    cudaFree(s->consisOut);
+    cudaFree(s->adapCmbPr);
+    cudaFree(s->consWt);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->flowUp[i]);
+        cudaFree(s->out_dev[i]);
+        cudaFreeHost(s->out_pin[i]);
+        if (s->out_conv[i]) cudaEventDestroy(s->out_conv[i]);
+        if (s->out_done[i]) cudaEventDestroy(s->out_done[i]);
+    }
+    cudaFree(s->ws);
+    if (s->compute) cudaStreamDestroy(s->compute);
+    if (s->copy) cudaStreamDestroy(s->copy);
+    if (s->d2h) cudaStreamDestroy(s->d2h);
+    (void)cudaGetLastError();
+    delete s;
+}
+
+extern "C" vsc_hyper_params* vsc_stabilizer_hyper_params(vsc_stabilizer* s) { return s ? &s->hp : nullptr; }
+
+extern "C" int vsc_stabilizer_push_frame(vsc_stabilizer* s, const uint8_t* orig_rgba_host,
+    const uint8_t* proc_rgba_host)
+{
+    if (!s || !orig_rgba_host || !proc_rgba_host)
+        return VSC_E_INVALID;
+    if (s->count >= 3)
+        return VSC_E_STATE;  // the window is full: call vsc_stabilizer_step first
+    const int k = (s->head + s->count) % kSlots;
+    const size_t bytes = s->P * 4;
+    int rc;
+    // the slot may still be read by an in-flight step (it was window[0] two steps ago)
+    if (s->slot_used[k] && (rc = cu(cudaStreamWaitEvent(s->copy, s->slot_released[k], 0))))
+        return rc;
+    const uint8_t* src[2] = {orig_rgba_host, proc_rgba_host};
+    float* dst[2] = {s->orig[k], s->proc[k]};
+    for (int i = 0; i < 2; ++i) {
+        const uint8_t* from = src[i];
+        if (!is_pinned(from)) {
+            if (s->slot_used[k])
+                cudaEventSynchronize(s->slot_h2d[k]);  // previous H2D out of this staging buffer (4 pushes ago)
+            std::memcpy(s->stage_pin[k][i], from, bytes);
+            from = s->stage_pin[k][i];
+        }
+        if ((rc = cu(cudaMemcpyAsync(s->stage_dev[k][i], from, bytes, cudaMemcpyHostToDevice, s->copy))))
+            return rc;
+    }
+    cudaEventRecord(s->slot_h2d[k], s->copy);
+    for (int i = 0; i < 2; ++i)
+        if ((rc = vsc_rgba8_to_f32x3(s->stage_dev[k][i], dst[i], s->W, s->H, s->copy)))
+            return rc;
+    s->pushed += 1;
+    if (s->pushed == 3) {
+        // preloadProcessedFrames: lastStabilizedFrame <- processedFrames.back() (videostabilizer.cpp:152).  The
+        // compute stream may still own lastStab only after a step, and none has run since create/reset.
+        if ((rc = cu(cudaMemcpyAsync(s->lastStab, s->proc[k], s->n * sizeof(float), cudaMemcpyDeviceToDevice,
+                 s->copy))))
+            return rc;
+    }
+    cudaEventRecord(s->slot_ready[k], s->copy);
+    s->slot_used[k] = true;
+    s->count += 1;
+    return cu(cudaGetLastError());
+}
+
+extern "C" int vsc_stabilizer_step(vsc_stabilizer* s, const float* flowFwd_dev, const float* flowBwd_dev,
+    uint8_t* out_rgba_host)
+{
+    if (!s || !flowFwd_dev || !flowBwd_dev)
+        return VSC_E_INVALID;
+    return do_step(s, flowFwd_dev, flowBwd_dev, out_rgba_host);
+}
+
+extern "C" int vsc_stabilizer_step_lowres_flow(vsc_stabilizer* s, const float* flowFwd_dev, const float* flowBwd_dev,
+    int flowW, int flowH, uint8_t* out_rgba_host)
+{
+    if (!s || !flowFwd_dev || !flowBwd_dev || flowW <= 0 || flowH <= 0)
+        return VSC_E_INVALID;
+    if (s->count != 3)
+        return VSC_E_STATE;
+    if (flowW == s->W && flowH == s->H)
+        return do_step(s, flowFwd_dev, flowBwd_dev, out_rgba_host);
+    // flowmodel.cpp:156-165: get_bilinear from the model's resolution, flow values not rescaled
+    int rc = vsc_bilinear(flowFwd_dev, flowW, flowH, s->flowC, s->flowUp[0], s->W, s->H, s->flowC, s->compute);
+    if (rc)
+        return rc;
+    rc = vsc_bilinear(flowBwd_dev, flowW, flowH, s->flowC, s->flowUp[1], s->W, s->H, s->flowC, s->compute);
+    if (rc)
+        return rc;
+    return do_step(s, s->flowUp[0], s->flowUp[1], out_rgba_host);
+}
+
+extern "C" int vsc_stabilizer_sync(vsc_stabilizer* s)
+{
+    if (!s)
+        return VSC_E_INVALID;
+    int rc = cu(cudaStreamSynchronize(s->copy));
+    if (!rc) rc = cu(cudaStreamSynchronize(s->compute));
+    if (!rc) rc = cu(cudaStreamSynchronize(s->d2h));
+    flush_pending(s, 0);
+    flush_pending(s, 1);
+    return rc;
+}
+
+extern "C" const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s) { return s ? s->lastStab : nullptr; }
+
+extern "C" int vsc_stabilizer_copy_last_output(vsc_stabilizer* s, float* dst_dev)
+{
+    if (!s || !dst_dev)
+        return VSC_E_INVALID;
+    return cu(cudaMemcpyAsync(dst_dev, s->lastStab, s->n * sizeof(float), cudaMemcpyDeviceToDevice, s->compute));
+}
+
+extern "C" vsc_stream_t vsc_stabilizer_compute_stream(vsc_stabilizer* s) { return s ? s->compute : nullptr; }
+
+extern "C" int vsc_stabilizer_reset(vsc_stabilizer* s)
+{
+    if (!s)
+        return VSC_E_INVALID;
+    const int rc = vsc_stabilizer_sync(s);
+    s->head = 0;
+    s->count = 0;
+    s->pushed = 0;
+    for (int k = 0; k < kSlots; ++k)
+        s->slot_used[k] = false;
+    return rc;
+}

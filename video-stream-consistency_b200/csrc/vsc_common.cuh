@@ -1,0 +1,58 @@
+// Shared helpers of the sm_100a kernels (internal; the public surface is include/vsc/vsc.h).
+//
+// Floating-point policy: the library is compiled with -fmad=false, so every expression is
+// evaluated exactly as written (IEEE fp32, round-to-nearest), which makes the small kernels
+// bit-identical to the plain-C restatement of the reference.  Fused multiply-adds appear only
+// where they are written explicitly (__fmaf_rn) in the two compute-heavy loops: the Correlation
+// contraction and the solver sweep.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vsc/vsc.h"
+
+namespace vsc {
+
+extern unsigned long long g_launches;  // host-side counter, see vsc_launch_count()
+
+inline void count_launch(unsigned n = 1) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+inline int launch_status()
+{
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? VSC_OK : static_cast<int>(e);
+}
+
+inline cudaStream_t as_stream(vsc_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+inline unsigned cdiv(long long a, long long b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// number of SMs of the current device (cached); B200 = 148
+int sm_count();
+
+// streaming (read-once) loads/stores: do not allocate in L1
+__device__ __forceinline__ float4 ldg_stream4(const float* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace vsc
