@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""bench.py -- stabilized frames/s of the per-frame hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one video frame through the hot path: the PWC-Net custom ops (Correlation + Warp at every
+decoder level, both flow directions), the flow upsample, and the full stabilization of the frame
+(fused warp x5 + adaptive combination + consistency weight, pyramid, screened-Poisson solve, 8-bit output).
+PWC-Net's dense convolutions stay in the reference's ORT graph and are out of scope (north_star); their
+activations are represented by synthetic device-resident feature / flow tensors of the right shapes.
+
+Workloads (BASELINE.json configs):
+  1080p-light  configs[1]: 1080p frames, pwcnet-light level shapes at FLOWDOWNSCALE=2, flow 960x540 upsampled  (default)
+  4k-dense     configs[2]: 4K frames, pwcnet dense level shapes at full resolution
+  4k-stab      configs[3]: precomputed-flow stabilization only at 4K
+
+value  = frames/s with every input already resident in HBM (CUDA events on the launching stream).
+e2e    = frames/s through the public pipeline object with HOST frame buffers: per step two RGBA8 frames are
+         uploaded from pinned memory and the stabilized RGBA8 frame is read back, inside the timed region.
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+Multi-GPU: independent streams, one per GPU (replicas; the recurrence is sequential per stream): value is the
+aggregate over ranks divided by the slowest rank's time; no data-path collective exists.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "video-stream-consistency_b200"), ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+LIGHT_CORR = [(196, 9, 15), (128, 18, 30), (96, 36, 60), (64, 72, 120)]
+LIGHT_WARP = [(128, 18, 30), (96, 36, 60), (64, 72, 120)]
+DENSE_CORR = [(196, 34, 60), (128, 68, 120), (96, 136, 240), (64, 272, 480), (32, 544, 960)]
+DENSE_WARP = [(128, 68, 120), (96, 136, 240), (64, 272, 480), (32, 544, 960)]
+
+WORKLOADS = {
+    "1080p-light": dict(W=1920, H=1080, flowW=960, flowH=540, corr=LIGHT_CORR, warp=LIGHT_WARP,
+                        desc="1080p frames, pwcnet-light custom-op level shapes at FLOWDOWNSCALE=2 (both directions), "
+                             "flow 960x540 upsampled, full stabilization (BASELINE configs[1])"),
+    "4k-dense": dict(W=3840, H=2160, flowW=3840, flowH=2160, corr=DENSE_CORR, warp=DENSE_WARP,
+                     desc="4K frames, pwcnet dense custom-op level shapes at full resolution (both directions), "
+                          "full stabilization (BASELINE configs[2])"),
+    "4k-stab": dict(W=3840, H=2160, flowW=3840, flowH=2160, corr=[], warp=[],
+                    desc="precomputed-flow stabilization only at 4K (BASELINE configs[3])"),
+}
+NFRAMES = 8  # distinct synthetic frame pairs, cycled
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id: str):
+        self.rows = []
+        self.proc = None
+        self.gpu_id = gpu_id
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", self.gpu_id], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def make_host_frames(W, H, pin):
+    import synth
+    import torch
+
+    o8, p8 = synth.frames(W, H, NFRAMES, seed=1234)
+    ho = [torch.from_numpy(np.ascontiguousarray(x)) for x in o8]
+    hp = [torch.from_numpy(np.ascontiguousarray(x)) for x in p8]
+    if pin:
+        ho = [x.pin_memory() for x in ho]
+        hp = [x.pin_memory() for x in hp]
+    return ho, hp
+
+
+def make_op_tensors(wl, dev):
+    """two independent sets (one per flow direction) of feature / flow tensors per decoder level"""
+    import synth
+    import torch
+
+    sets = []
+    for d in range(2):
+        corr = [(torch.from_numpy(synth.features(1, C, h, w, 10 * d + i)).to(dev),
+                 torch.from_numpy(synth.features(1, C, h, w, 10 * d + i + 5)).to(dev),
+                 torch.empty((1, 9, 9, h, w), device=dev)) for i, (C, h, w) in enumerate(wl["corr"])]
+        warp = [(torch.from_numpy(synth.features(1, C, h, w, 20 * d + i)).to(dev),
+                 torch.from_numpy(synth.op_flow(1, h, w, 30 * d + i)).to(dev),
+                 torch.empty((1, C, h, w), device=dev)) for i, (C, h, w) in enumerate(wl["warp"])]
+        sets.append((corr, warp))
+    return sets
+
+
+def op_bytes(wl):
+    b = 0
+    for C, h, w in wl["corr"]:
+        b += 4 * h * w * (2 * C + 81)
+    for C, h, w in wl["warp"]:
+        b += 4 * h * w * (2 * C + 2)
+    return 2 * b  # both directions
+
+
+def run_ops(V, sets):
+    for corr, warp in sets:
+        for a, b, o in corr:
+            V.correlation(a, b, out=o)
+        for x, f, o in warp:
+            V.warp(x, f, out=o)
+
+
+# ------------------------------------------------------------------------------------------------ ranks
+def reduce_over_ranks(times_ms, counts, world, device):
+    """replica scaling: every rank runs an independent stream; the job time is the MAX over ranks, counters add.
+    (torch.distributed is used for this bookkeeping and the barriers only -- the data path has no collective.)"""
+    if world <= 1:
+        return list(times_ms), list(counts)
+    import torch
+    import torch.distributed as dist
+
+    tt = torch.tensor(list(times_ms), device=device, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    cc = torch.tensor(list(counts), device=device, dtype=torch.int64)
+    dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+    return [float(x) for x in tt], [int(x) for x in cc]
+
+
+def aggregate_fps(world, steps, ms):
+    """whole-job throughput: all ranks' frames divided by the slowest rank's time"""
+    return world * steps / (ms * 1e-3)
+
+
+def stream_frame_index(t):
+    """window (prev, cur, next) of step t over the cycled synthetic frames"""
+    return (t - 1) % NFRAMES, t % NFRAMES, (t + 1) % NFRAMES
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def bench_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import synth
+    import vsc_b200 as V
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    W, H, fw, fh = wl["W"], wl["H"], wl["flowW"], wl["flowH"]
+    K, Wm = args.steps, args.warmup
+    peaks, peak_src = measured_peaks()
+
+    ho, hp = make_host_frames(W, H, pin=True)
+    flf, flb = synth.flows(fw, fh, 3)
+    d_flf, d_flb = torch.from_numpy(flf).to(dev), torch.from_numpy(flb).to(dev)
+    sets = make_op_tensors(wl, dev)
+    hpar = V.HyperParams()
+
+    # ---------------- device-resident arm: every input already in HBM ----------------
+    d_o = [V.image_to_gpu(x.to(dev)) for x in ho]
+    d_p = [V.image_to_gpu(x.to(dev)) for x in hp]
+    last = d_p[2].clone()
+    cons = torch.empty_like(last)
+    ws = torch.empty(int(V.lib().vsc_frame_solve_workspace_bytes(W, H, hpar.pyramidLevels)), device=dev,
+                     dtype=torch.uint8)
+    lowres = (fw, fh) != (W, H)
+    upf = torch.empty((H, W, 3), device=dev) if lowres else d_flf
+    upb = torch.empty((H, W, 3), device=dev) if lowres else d_flb
+    import ctypes as C
+
+    L = V.lib()
+
+    def dptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    def stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    out8 = torch.empty((H, W, 4), device=dev, dtype=torch.uint8)
+
+    def step_resident(t):
+        nonlocal last, cons
+        run_ops(V, sets)
+        if lowres:
+            V.check(L.vsc_bilinear(dptr(d_flf), fw, fh, 3, dptr(upf), W, H, 3, stream()))
+            V.check(L.vsc_bilinear(dptr(d_flb), fw, fh, 3, dptr(upb), W, H, 3, stream()))
+        i0, i1, i2 = stream_frame_index(t)
+        _, aP, wt = V.stage_a_fused(d_o[i0], d_o[i1], d_o[i2], d_p[i0], d_p[i1], d_p[i2], last, upf, upb,
+                                    hpar.alpha, hpar.beta, hpar.gamma)
+        V.frame_solve(d_p[i1], aP, wt, hpar, workspace=ws, out=cons)
+        V.check(L.vsc_f32x3_to_rgba8(dptr(cons), dptr(out8), W, H, stream()))
+        last, cons = cons, last
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(Wm):
+        step_resident(1 + t)
+    barrier()
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_id = str(local)
+    clocks = ClockSampler(gpu_id)
+    clocks.start()
+    time.sleep(0.25)
+    n0 = V.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    for t in range(K):
+        step_resident(1 + Wm + t)
+    e1.record()
+    barrier()
+    t_host1 = time.perf_counter()
+    launches = V.launch_count() - n0
+    ms_res = e0.elapsed_time(e1)
+
+    # ---------------- end-to-end arm: host frame buffers through the pipeline object ----------------
+    st = V.Stabilizer(W, H, 3)
+    outs = [V.pinned_empty((H, W, 4)) for _ in range(2)]
+    ext = torch.cuda.ExternalStream(st.compute_stream, device=dev)
+
+    def step_e2e(t):
+        with torch.cuda.stream(ext):  # custom ops share the pipeline's compute stream
+            run_ops(V, sets)
+        st.step(d_flf, d_flb, outs[t & 1])
+        st.push_frame(ho[(t + 2) % NFRAMES], hp[(t + 2) % NFRAMES])
+
+    for t in range(3):
+        st.push_frame(ho[t], hp[t])
+    for t in range(Wm):
+        step_e2e(1 + t)
+    st.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(K):
+        step_e2e(1 + Wm + t)
+    st.sync()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ms_e2e = (t1 - t0) * 1e3
+    clk = clocks.stop(t_host0, t1)
+    st.close()
+
+    # ---------------- roofline of the dominant kernel: one solver sweep at level 0 ----------------
+    # marginal time of a sweep = (t(2n sweeps) - t(n sweeps)) / n, CUDA events on the launching stream
+    def time_solve(iters):
+        x = d_p[1].clone()
+        wsb = torch.empty(int(L.vsc_consist_solve_workspace_bytes(W, H)), device=dev, dtype=torch.uint8)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        V.check(L.vsc_consist_solve(dptr(d_p[1]), dptr(d_p[2]), dptr(d_o[1]), iters, C.c_float(0.15), C.c_float(0.15),
+                                    dptr(x), W, H, dptr(wsb), C.c_size_t(wsb.numel()), stream()))
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
+
+    time_solve(10)
+    n = hpar.numIter
+    sweep_ms = (time_solve(2 * n) - time_solve(n)) / n
+    alg_bytes = 72.0 * W * H  # 72 B/pixel/sweep (out,u,A,B read; out,u written)
+    achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get("solver_sweep_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---------------- aggregate over ranks (max time) ----------------
+    (ms_res, ms_e2e), (launches,) = reduce_over_ranks([ms_res, ms_e2e], [launches], world, dev)
+
+    result = None
+    if rank == 0:
+        cpu = cpu_baseline(wl, args) if world == 1 and not args.no_cpu_baseline else None
+        result = {
+            "metric": "stabilized_frames_per_sec", "value": aggregate_fps(world, K, ms_res), "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_res / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "resolution": f"{W}x{H}",
+                       "flow_resolution": f"{fw}x{fh}", "numIter": hpar.numIter, "pyramidLevels": hpar.pyramidLevels,
+                       "streams": world, "parallelism": f"replicas x{world} (independent video streams, no collective)",
+                       "l2": f"inputs larger than L2: {NFRAMES} frame pairs cycled, per-step working set "
+                             f"{(12 * 4 + 6 * 4) * W * H / 1e6:.0f} MB of solver state > 126 MB L2" if W * H * 72 > 126e6
+                       else f"{NFRAMES} frame pairs cycled; solver state {72 * W * H / 1e6:.0f} MB per sweep",
+                       "custom_op_bytes_per_step": op_bytes(wl),
+                       "out_of_scope": "PWC-Net convolutions (ORT graph): synthetic device-resident activations"},
+            "e2e": {"value": aggregate_fps(world, K, ms_e2e), "unit": "frames/s", "h2d_bytes_per_step": 2 * W * H * 4,
+                    "d2h_bytes_per_step": W * H * 4, "timing": "host clock between full device synchronisations",
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "solver_sweep_vec_kernel (level 0, one Jacobi sweep)", "bound": "hbm",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": sweep_ms * 1e3,
+                         "peak_source": peak_src},
+        }
+        if cpu:
+            result["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_frame(O, wl, band_h, state):
+    """one frame (or a horizontal band of it) of the hot path on the host: reference CPU custom ops
+    (oracle/_ref, the reference's own kernels, 1 thread as built) + the oracle port of the stabilization
+    (the reference has no CPU stabilization code), OpenMP over all cores."""
+    for d in range(2):
+        for a, b in state["corr"][d]:
+            state["corr_fn"](a, b)
+        for x, f in state["warp"][d]:
+            state["warp_fn"](x, f)
+    of, pf, ff, fb = state["of"], state["pf"], state["ff"], state["fb"]
+    co, _ = O.do_one_step(of[0], of[1], of[2], pf[0], pf[1], pf[2], state["last"], ff, fb)
+    state["last"] = co
+
+
+def cpu_state(O, wl, band_h):
+    import synth
+
+    W, H = wl["W"], band_h
+    o8, p8 = synth.frames(W, H, 3, seed=1234)
+    ffl, fbl = synth.flows(W, H, 3)
+    st = {"of": [O.rgba8_to_f32x3(x) for x in o8], "pf": [O.rgba8_to_f32x3(x) for x in p8], "ff": ffl, "fb": fbl}
+    st["last"] = st["pf"][2]
+    use_ref = O.ref_cpu_available()
+    st["corr_fn"] = O.ref_cpu_correlation if use_ref else O.correlation
+    st["warp_fn"] = O.ref_cpu_warp if use_ref else O.warp_nchw
+    st["ops_kind"] = "reference (oracle/_ref, 1 thread as built)" if use_ref else "oracle port"
+    frac = band_h / wl["H"]
+    st["corr"], st["warp"] = [], []
+    for d in range(2):
+        st["corr"].append([(synth.features(1, C, max(1, round(h * frac)), w, d + i),
+                            synth.features(1, C, max(1, round(h * frac)), w, d + i + 7))
+                           for i, (C, h, w) in enumerate(wl["corr"])])
+        st["warp"].append([(synth.features(1, C, max(1, round(h * frac)), w, d + i),
+                            synth.op_flow(1, max(1, round(h * frac)), w, d + i + 9))
+                           for i, (C, h, w) in enumerate(wl["warp"])])
+    return st
+
+
+def cpu_baseline(wl, args, frames=None, band_h=None):
+    from oracle import oracle as O
+
+    H = wl["H"]
+    band_h = band_h or (H if wl["W"] * H <= 1920 * 1080 else H // 4)
+    band_h -= band_h % 2
+    st = cpu_state(O, wl, band_h)
+    cpu_frame(O, wl, band_h, st)  # warm-up
+    n = frames or (5 if band_h == H and H <= 1080 else 4)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        cpu_frame(O, wl, band_h, st)
+    dt = time.perf_counter() - t0
+    fps = n / dt * (band_h / H)
+    return {"value": fps, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{n} frames of a {wl['W']}x{band_h} band ({band_h}/{H} of the frame, scaled linearly); "
+                      f"stabilization = oracle port (OpenMP, {O.num_threads()} threads; the reference has no CPU "
+                      f"stabilization code); custom ops = {st['ops_kind']}",
+            "seconds": dt}
+
+
+def bench_reference(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+
+    wl = WORKLOADS[args.workload]
+    K, Wm = args.steps, args.warmup
+    H = wl["H"]
+    # bounded sample: a full 1080p frame costs ~2 s on 8 cores; keep the whole run within a few minutes
+    budget_frames = 40.0 * (1920 * 1080) / (wl["W"] * H)
+    band_h = H if (K + Wm) <= budget_frames else max(32, int(H * budget_frames / (K + Wm)))
+    band_h -= band_h % 2
+    st = cpu_state(O, wl, band_h)
+    for _ in range(Wm):
+        cpu_frame(O, wl, band_h, st)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        cpu_frame(O, wl, band_h, st)
+    dt = time.perf_counter() - t0
+    fps = K / dt * (band_h / H)
+    sample = (f"each step = one {wl['W']}x{band_h} band ({band_h}/{H} of a frame, throughput scaled linearly); "
+              f"stabilization = oracle port (OpenMP {O.num_threads()} threads; no reference CPU code exists), "
+              f"custom ops = {st['ops_kind']}")
+    return {
+        "impl": "reference", "metric": "stabilized_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dt / K * 1e3 / (band_h / H),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "resolution": f"{wl['W']}x{H}",
+                   "numIter": 150, "pyramidLevels": 2},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p-light", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        res = bench_reference(args, rank, world)
+    else:
+        res = bench_ours(args, rank, world)
+    if rank == 0 and res is not None:
+        print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

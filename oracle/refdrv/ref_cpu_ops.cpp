@@ -2,7 +2,7 @@
 //
 // Driver that runs the reference's OWN CPU custom-op kernels
 // (/root/reference/src/ort_custom_ops/src/opticalflow/{correlation,warp}.cc, compiled
-// unmodified against the stand-in ORT headers in oracle/shim/ort) on plain host
+// unmodified against the stand-in ORT headers in standins/ort) on plain host
 // buffers.  It goes through CorrelationKernel::Compute / WarpKernel::Compute
 // (correlation.h:33-49, warp.h:18-31), i.e. through the same shape logic and
 // attribute handling ORT would exercise.  Built by oracle/Makefile into
@@ -10,10 +10,12 @@
 // pinning) and by bench.py's cpu_baseline / --impl reference legs only.
 #include <ort_custom_ops/opticalflow/correlation.h>
 #include <ort_custom_ops/opticalflow/warp.h>
+#include <ort_custom_ops/custom_ops.h>
 
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#include <string>
 
 namespace {
 
@@ -89,6 +91,36 @@ int vsc_ref_cpu_warp(const float* in, const float* flow, float* out, size_t out_
         std::fprintf(stderr, "vsc_ref_cpu_warp: %s\n", e.what());
         return 1;
     }
+}
+
+// the reference's own registration (custom_ops.cpp:73-97) against the stand-in session:
+// "domain|op|provider|nin|nout|intype0|outtype0;" per registered op; returns the number of ops, -1 on error
+int vsc_ref_cpu_registry(char* buf, size_t n)
+{
+    static OrtSessionOptions opts;
+    static bool done = false;
+    if (!done) {
+        done = true;
+        Ort::InitApi(OrtGetApiBase()->GetApi(ORT_API_VERSION));  // the host's auto-initialised copy, SURVEY 8b pitfall
+        if (OrtStatus* st = RegisterCustomOps(&opts, OrtGetApiBase())) {
+            std::fprintf(stderr, "reference RegisterCustomOps: %s\n", st->msg.c_str());
+            delete st;
+            return -1;
+        }
+    }
+    std::string s;
+    int count = 0;
+    for (OrtCustomOpDomain* d : opts.domains)
+        for (const OrtCustomOp* op : d->ops) {
+            char line[256];
+            std::snprintf(line, sizeof line, "%s|%s|%s|%zu|%zu|%d|%d;", d->name.c_str(), op->GetName(op),
+                op->GetExecutionProviderType(op), op->GetInputTypeCount(op), op->GetOutputTypeCount(op),
+                static_cast<int>(op->GetInputType(op, 0)), static_cast<int>(op->GetOutputType(op, 0)));
+            s += line;
+            ++count;
+        }
+    std::snprintf(buf, n, "%s", s.c_str());
+    return count;
 }
 
 // missing-attribute behaviour of the reference ctor (correlation.h:19-31): returns 1 if it threw

@@ -6,7 +6,7 @@
 // stabilization kernels (flowconsistency.cu, gpuimage.{cu,cpp}) through the six
 // free functions of flowconsistency.cuh.  All reference files are compiled
 // UNMODIFIED from /root/reference for sm_100a (oracle/Makefile) against the
-// stand-in headers of oracle/shim.  The per-frame call sequence of
+// stand-in headers of standins/.  The per-frame call sequence of
 // VideoStabilizer::doOneStep (videostabilizer.cpp:167-265) cannot be compiled
 // (Qt containers) and is restated in vsc_ref_gpu_do_one_step below, calling the
 // reference's functions in the reference's order.

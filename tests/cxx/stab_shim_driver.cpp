@@ -1,0 +1,148 @@
+// TEST DRIVER for the product's stabilization shim (video-stream-consistency_b200/host/stabilization):
+// the same role VideoStabilizer plays in the reference -- it owns GPUImage objects, fills them from RGBA host
+// frames through GPUImage::copyFromQImage, and runs the doOneStep call sequence (videostabilizer.cpp:177-247)
+// through the six flowconsistency.cuh functions, which here resolve to the shim (i.e. to libvsc_b200.so).
+// Compiled against the reference's unmodified gpuimage.h / flowconsistency.cuh and the QImage stand-in.
+#include "flowconsistency.cuh"
+#include "gpuimage.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <vector>
+
+namespace {
+struct Stab {
+    int W = 0, H = 0, flowC = 3, k = 0;
+    std::vector<std::unique_ptr<GPUImage>> orig, proc;  // sliding window, front = prev
+    std::unique_ptr<GPUImage> last, flowFwd, flowBwd, prevWarpIn, prevWarpPr, nextWarpIn, nextWarpPr, lastStabWarp,
+        consisOut, consWt, adapCmbIn, adapCmbPr;
+    std::vector<std::unique_ptr<GPUImage>> pyrPr, pyrAdapCmbPr, pyrConsWt, pyrConsisOut;
+};
+std::unique_ptr<GPUImage> mk(int w, int h, int c) { return std::unique_ptr<GPUImage>(new GPUImage(w, h, c)); }
+}  // namespace
+
+extern "C" {
+
+void* vsc_shim_create(int W, int H, int flowC, int levels)
+{
+    try {
+        Stab* s = new Stab;
+        s->W = W;
+        s->H = H;
+        s->flowC = flowC;
+        s->last = mk(W, H, 3);
+        s->flowFwd = mk(W, H, flowC);
+        s->flowBwd = mk(W, H, flowC);
+        s->prevWarpIn = mk(W, H, 3);
+        s->prevWarpPr = mk(W, H, 3);
+        s->nextWarpIn = mk(W, H, 3);
+        s->nextWarpPr = mk(W, H, 3);
+        s->lastStabWarp = mk(W, H, 3);
+        s->consisOut = mk(W, H, 3);
+        s->consWt = mk(W, H, 3);
+        s->adapCmbIn = mk(W, H, 3);
+        s->adapCmbPr = mk(W, H, 3);
+        int pw = W, ph = H;
+        for (int i = 0; i < levels; ++i) {
+            s->pyrPr.push_back(mk(pw, ph, 3));
+            s->pyrAdapCmbPr.push_back(mk(pw, ph, 3));
+            s->pyrConsWt.push_back(mk(pw, ph, 3));
+            s->pyrConsisOut.push_back(mk(pw, ph, 3));
+            pw /= 2;
+            ph /= 2;
+        }
+        return s;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_shim_create: %s\n", e.what());
+        return nullptr;
+    }
+}
+
+void vsc_shim_destroy(void* p) { delete static_cast<Stab*>(p); }
+
+// loadFrame: imageToGPU x2 (imagehelpers.cpp:16-20); the third frame also seeds lastStabilizedFrame (:152)
+int vsc_shim_push(void* p, const unsigned char* orig_rgba, const unsigned char* proc_rgba)
+{
+    try {
+        Stab& s = *static_cast<Stab*>(p);
+        QImage qo(s.W, s.H, QImage::Format_RGBA8888), qp(s.W, s.H, QImage::Format_RGBA8888);
+        std::memcpy(qo.bits(), orig_rgba, static_cast<size_t>(s.W) * s.H * 4);
+        std::memcpy(qp.bits(), proc_rgba, static_cast<size_t>(s.W) * s.H * 4);
+        auto o = mk(s.W, s.H, 3), q = mk(s.W, s.H, 3);
+        o->copyFromQImage(qo);
+        q->copyFromQImage(qp);
+        s.orig.push_back(std::move(o));
+        s.proc.push_back(std::move(q));
+        if (s.proc.size() == 3 && s.k == 0) {
+            s.last->copyFrom(*s.proc.back());
+            s.k = 1;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_shim_push: %s\n", e.what());
+        return 1;
+    }
+}
+
+int vsc_shim_step(void* p, const float* flowFwd_host, const float* flowBwd_host, float alpha, float beta, float gamma,
+    int numIter, float stepSize, float momFac, unsigned char* rgba_out, float* consis_out_host)
+{
+    try {
+        Stab& s = *static_cast<Stab*>(p);
+        if (s.orig.size() != 3)
+            return 3;
+        const int W = s.W, H = s.H;
+        std::vector<float> ff(flowFwd_host, flowFwd_host + static_cast<size_t>(W) * H * s.flowC);
+        std::vector<float> fb(flowBwd_host, flowBwd_host + static_cast<size_t>(W) * H * s.flowC);
+        s.flowFwd->copyFrom(ff);
+        s.flowBwd->copyFrom(fb);
+        get_warp_result(*s.orig[0], *s.flowBwd, *s.prevWarpIn);
+        get_warp_result(*s.proc[0], *s.flowBwd, *s.prevWarpPr);
+        get_warp_result(*s.orig[2], *s.flowFwd, *s.nextWarpIn);
+        get_warp_result(*s.proc[2], *s.flowFwd, *s.nextWarpPr);
+        get_warp_result(*s.last, *s.flowBwd, *s.lastStabWarp);
+        get_adap_comb(*s.orig[1], *s.proc[1], *s.prevWarpIn, *s.prevWarpPr, *s.nextWarpIn, *s.nextWarpPr, *s.adapCmbIn,
+            *s.adapCmbPr, *s.lastStabWarp, alpha);
+        get_consist_wt(*s.adapCmbIn, *s.orig[1], *s.consWt, beta, gamma);
+        const int levels = static_cast<int>(s.pyrPr.size());
+        for (int j = 0; j < levels; ++j) {
+            if (j == 0) {
+                s.pyrPr[0]->copyFrom(*s.proc[1]);
+                s.pyrAdapCmbPr[0]->copyFrom(*s.adapCmbPr);
+                s.pyrConsWt[0]->copyFrom(*s.consWt);
+                s.pyrConsisOut[0]->copyFrom(*s.proc[1]);
+            } else {
+                get_bilinear(*s.pyrPr[j - 1], *s.pyrPr[j]);
+                get_bilinear(*s.pyrAdapCmbPr[j - 1], *s.pyrAdapCmbPr[j]);
+                get_bilinear(*s.pyrConsWt[j - 1], *s.pyrConsWt[j]);
+                get_bilinear(*s.pyrConsisOut[j - 1], *s.pyrConsisOut[j]);
+            }
+        }
+        for (int j = levels - 1; j >= 0; --j) {
+            if (j != levels - 1)
+                get_bilinear(*s.pyrConsisOut[j + 1], *s.pyrConsisOut[j]);
+            get_consist_out(*s.pyrPr[j], *s.pyrAdapCmbPr[j], *s.pyrConsWt[j], numIter / (j + 1), stepSize, momFac,
+                *s.pyrConsisOut[j]);
+        }
+        s.consisOut->copyFrom(*s.pyrConsisOut[0]);
+        if (rgba_out) {
+            QImage q(W, H, QImage::Format_RGBA8888);
+            s.consisOut->copyToQImage(q);
+            std::memcpy(rgba_out, q.bits(), static_cast<size_t>(W) * H * 4);
+        }
+        if (consis_out_host)
+            cudaMemcpy(consis_out_host, s.consisOut->data, sizeof(float) * 3 * W * H, cudaMemcpyDeviceToHost);
+        s.last->copyFrom(*s.consisOut);
+        s.orig.erase(s.orig.begin());
+        s.proc.erase(s.proc.begin());
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_shim_step: %s\n", e.what());
+        return 1;
+    }
+}
+}

@@ -89,3 +89,4 @@ def build(force: bool = False, ptxas_v: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, ptxas_v="--ptxas-v" in sys.argv))
+
