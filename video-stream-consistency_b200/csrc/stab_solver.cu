@@ -139,8 +139,9 @@ __global__ void __launch_bounds__(256) copy_kernel(const float* __restrict__ src
 }
 
 struct SolveBuffers {
-    float *coefA, *coefB, *u, *alt;
+    float *coefA, *coefB, *u, *alt, *u2;  // u2: second momentum buffer for the temporally blocked passes
 };
+constexpr int kSolveArrays = 5;
 
 static SolveBuffers carve(void* ws, size_t n)
 {
@@ -151,6 +152,7 @@ static SolveBuffers carve(void* ws, size_t n)
     b.coefB = reinterpret_cast<float*>(p + s);
     b.u = reinterpret_cast<float*>(p + 2 * s);
     b.alt = reinterpret_cast<float*>(p + 3 * s);
+    b.u2 = reinterpret_cast<float*>(p + 4 * s);
     return b;
 }
 
@@ -163,27 +165,64 @@ static int launch_prepare(const float* pr, const float* tgt, const float* wt, co
     return launch_status();
 }
 
-// `iters` sweeps starting from the state in x; returns through *result the buffer holding the result
+// implemented in stab_solver_stream.cu: T sweeps per launch, T in {8, 4}
+int solver_stream_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
+    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st);
+
+int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
+
+// how `iters` sweeps are executed: n8 passes of 8 sweeps, n4 passes of 4, `rest` single unblocked sweeps
+struct SweepPlan {
+    int n8, n4, rest;
+    int flips() const { return n8 + n4 + rest; }  // number of out-buffer ping-pongs
+};
+
+static SweepPlan plan_sweeps(int W, int H, int iters)
+{
+    SweepPlan p{0, 0, iters};
+    // tiny images: the 3T-step pipeline fill and the 6T-float band halo dominate -> plain sweeps
+    const bool big = H >= 48 && 3 * W >= 384;
+    if (g_solver_mode == 1 || (g_solver_mode == 0 && !big))
+        return p;
+    p.n8 = iters / 8;
+    p.n4 = (iters % 8) / 4;
+    p.rest = iters % 4;
+    return p;
+}
+
+// `iters` sweeps starting from the state in x (momentum in b.u, zeroed by the prepare kernel); the result
+// lands in x if plan.flips() is even, else in y
 static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, int iters, float step, float mom,
     cudaStream_t st, float** result)
 {
-    const bool vec = (3LL * W) % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(b.coefA) && aligned16(b.coefB)
-        && aligned16(b.u);
+    const SweepPlan plan = plan_sweeps(W, H, iters);
     float* src = x;
     float* dst = y;
-    for (int k = 0; k < iters; ++k) {
+    float* us = b.u;
+    float* ud = b.u2;
+    int rc = VSC_OK;
+    for (int k = 0; k < plan.n8 + plan.n4 && rc == VSC_OK; ++k) {
+        rc = solver_stream_pass(k < plan.n8 ? 8 : 4, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
+        float* t = src; src = dst; dst = t;
+        t = us; us = ud; ud = t;
+    }
+    if (rc != VSC_OK)
+        return rc;
+    const bool vec = (3LL * W) % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(b.coefA) && aligned16(b.coefB)
+        && aligned16(us);
+    for (int k = 0; k < plan.rest; ++k) {
         if (vec) {
             const dim3 grid(cdiv(3LL * W / 4, 128), H);
-            solver_sweep_vec_kernel<<<grid, 128, 0, st>>>(b.coefA, b.coefB, b.u, src, dst, W, H, step, mom);
+            solver_sweep_vec_kernel<<<grid, 128, 0, st>>>(b.coefA, b.coefB, us, src, dst, W, H, step, mom);
         } else {
             const dim3 grid(cdiv(3LL * W, 256), H);
-            solver_sweep_scalar_kernel<<<grid, 256, 0, st>>>(b.coefA, b.coefB, b.u, src, dst, W, H, step, mom);
+            solver_sweep_scalar_kernel<<<grid, 256, 0, st>>>(b.coefA, b.coefB, us, src, dst, W, H, step, mom);
         }
         float* t = src;
         src = dst;
         dst = t;
     }
-    count_launch(iters);
+    count_launch(plan.rest);
     *result = src;
     return launch_status();
 }
@@ -196,7 +235,7 @@ extern "C" size_t vsc_consist_solve_workspace_bytes(int W, int H)
 {
     if (W <= 0 || H <= 0)
         return 0;
-    return 4 * align_up(static_cast<size_t>(W) * H * 3 * sizeof(float));
+    return kSolveArrays * align_up(static_cast<size_t>(W) * H * 3 * sizeof(float));
 }
 
 extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, const float* consWt, int numIter,
@@ -212,8 +251,8 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
     cudaStream_t st = as_stream(stream);
     const size_t n = static_cast<size_t>(W) * H * 3;
     const SolveBuffers b = carve(workspace, n);
-    // start in the buffer that makes the last sweep land in consisOut
-    const bool odd = (numIter & 1) != 0;
+    // start in the buffer that makes the last sweep (or blocked pass) land in consisOut
+    const bool odd = (plan_sweeps(W, H, numIter).flips() & 1) != 0;
     int rc = launch_prepare(crntPr, prevStabWarp, consWt, b, odd ? consisOut : nullptr, odd ? b.alt : nullptr, W, H,
         stepSize, st);
     if (rc)
@@ -221,6 +260,14 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
     float* res = nullptr;
     rc = run_sweeps(b, odd ? b.alt : consisOut, odd ? consisOut : b.alt, W, H, numIter, stepSize, momFac, st, &res);
     return rc;
+}
+
+extern "C" int vsc_set_solver_mode(int mode)
+{
+    if (mode < 0 || mode > 2)
+        return VSC_E_INVALID;
+    g_solver_mode = mode;
+    return VSC_OK;
 }
 
 extern "C" void vsc_hyper_params_default(vsc_hyper_params* p)
@@ -262,9 +309,9 @@ extern "C" size_t vsc_frame_solve_workspace_bytes(int W, int H, int pyramidLevel
     if (W <= 0 || H <= 0 || pyramidLevels < 1 || pyramidLevels > kMaxLevels)
         return 0;
     const LevelDims d = level_dims(W, H, pyramidLevels);
-    size_t total = 4 * align_up(d.n[0] * sizeof(float));  // level 0: A, B, u, alt
+    size_t total = kSolveArrays * align_up(d.n[0] * sizeof(float));  // level 0: A, B, u, alt, u2
     for (int j = 1; j < pyramidLevels; ++j)
-        total += 8 * align_up((d.n[j] ? d.n[j] : 1) * sizeof(float));  // pr, tgt, wt, out + A, B, u, alt
+        total += (4 + kSolveArrays) * align_up((d.n[j] ? d.n[j] : 1) * sizeof(float));  // pr, tgt, wt, out + 5
     return total;
 }
 
@@ -292,7 +339,7 @@ extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, con
     const float* wt[kMaxLevels];
     float* out[kMaxLevels];
     sb[0] = carve(ws, d.n[0]);
-    ws += 4 * align_up(d.n[0] * sizeof(float));
+    ws += kSolveArrays * align_up(d.n[0] * sizeof(float));
     pr[0] = procCur;
     tg[0] = adapCmbPr;
     wt[0] = consWt;
@@ -305,7 +352,7 @@ extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, con
         wt[j] = reinterpret_cast<float*>(ws + 2 * s);
         out[j] = reinterpret_cast<float*>(ws + 3 * s);
         sb[j] = carve(ws + 4 * s, d.n[j]);
-        ws += 8 * s;
+        ws += (4 + kSolveArrays) * s;
     }
 
     int rc;
@@ -324,7 +371,7 @@ extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, con
     float* coarse_result = nullptr;
     for (int j = levels - 1; j >= 0; --j) {
         const int iters = p->numIter / (j + 1);
-        const bool odd = (iters & 1) != 0;
+        const bool odd = (plan_sweeps(d.w[j], d.h[j], iters).flips() & 1) != 0;
         // x = buffer holding the initial state, y = the other one; the result lands in `final`
         float* final_buf = (j == 0) ? consisOut : out[j];
         float* x = odd ? sb[j].alt : final_buf;

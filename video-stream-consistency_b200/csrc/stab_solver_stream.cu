@@ -1,0 +1,203 @@
+// Temporally blocked solver sweep for sm_100a: T Jacobi sweeps of the screened-Poisson update per launch,
+// with every intermediate sweep kept on chip (reference loop: flowconsistency.cu:367-372, one launch and one
+// full HBM round trip of 7 images per sweep).
+//
+// The unblocked sweep (stab_solver.cu) already runs at the HBM roofline, so the only way to go faster is to
+// not touch HBM between sweeps.  Scheme (validated bit-for-bit against plain Jacobi by the NumPy emulation in
+// tests/emul_stream_solver.py, of which this kernel is a transliteration):
+//
+//   * the image is the 2-D float array [H][L], L = 3W (interleaved channels; x-neighbours are +-3 floats);
+//   * a CTA owns a band of BW = blockDim.x consecutive floats and STREAMS down a chunk of rows; thread `tid`
+//     owns column g0+tid for ALL T time levels, held in registers:
+//         win[t][4]  level-t values of the last 4 rows      uu[t][4]  the matching momentum terms
+//         Ar/Br[2T]  the folded coefficients of the last 2T rows
+//   * at step s the level-0 row y_in = r0-T+s arrives from HBM; level t (1..T) computes row y_in-2t from the
+//     level t-1 rows y_in-2t-1 .. y_in-2t+1, which level t-1 produced at steps s-3, s-2, s-1.  The skew of
+//     TWO rows per level makes the T updates of a step mutually independent: ONE barrier per step, T
+//     independent dependency chains per thread (ILP), no redundant work in y inside a chunk;
+//   * level-0 rows (out, u, A, B) are fetched 8 steps ahead with cp.async into a thread-private staging ring
+//     (HBM latency is several steps long; with a 1-step register prefetch the kernel was latency-bound and
+//     slower than the unblocked sweeps -- profiles/r1_notes.md);
+//   * up/down neighbours are the thread's own registers; left/right neighbours (+-3 floats, other threads)
+//     come from a shared-memory ring written two steps earlier: 2 LDS.32 + 1 STS.32 per value and sweep;
+//   * level-T rows inside the chunk and inside the band's valid cone (3T floats from each band edge, T rows
+//     from each chunk edge are halo) are stored.  HBM traffic per sweep drops from 24 B/value to
+//     ~24/(T * efficiency) B/value; efficiency = (1-6T/BW) * rows/(rows+3T) ~ 0.8 at T=8, BW=512.
+//
+// Rings are indexed by (step mod 4) / (step mod 2T); the step loop is unrolled 2T times so every ring index
+// is a compile-time constant and the rings live in registers without moves.
+#include "vsc_common.cuh"
+
+namespace vsc {
+
+constexpr int kStreamThreads = 512;
+constexpr int kStreamPrefetch = 8;  // must divide the unroll factor 2T (T in {4, 8})
+
+template <int T>
+__global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const float* __restrict__ coefA,
+    const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
+    const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
+{
+    constexpr int BW = kStreamThreads;
+    constexpr int S = BW - 6 * T;   // columns stored per band
+    constexpr int U = 2 * T;        // unroll: lcm(4, 2T) for T in {4, 8}
+    static_assert(U % 4 == 0, "ring period");
+    constexpr int PF = kStreamPrefetch;  // rows in flight from HBM
+    extern __shared__ float smem_raw[];
+    float* sm = smem_raw + 4;  // 4 floats of padding on each side: tid-3 / tid+3 never leave the allocation
+    // thread-private staging ring for the level-0 rows: stage[slot][array][tid], filled by cp.async PF steps
+    // ahead (each thread copies and later reads only its own 4 floats per row: no cross-thread ordering needed)
+    float* stage = smem_raw + T * 4 * BW + 8;
+
+    const int tid = threadIdx.x;
+    const int L = 3 * W;
+    const int g0 = blockIdx.x * S - 3 * T;
+    const int gi = g0 + tid;
+    const int r0 = blockIdx.y * chunk_rows;
+    const int r1 = min(H, r0 + chunk_rows);
+    const bool col_ok = gi >= 0 && gi < L;
+    const bool store_col = col_ok && tid >= 3 * T && tid < 3 * T + S;
+    const bool m_r = gi < 3 * (W - 2);  // right neighbour included  <=>  x+1 < W-1   (flowconsistency.cu:215)
+    const bool m_l = gi >= 3;           // left neighbour included   <=>  x-1 >= 0    (:221)
+    const int nsteps = (r1 - r0) + 3 * T;
+    const size_t colofs = static_cast<size_t>(col_ok ? gi : 0);
+
+    float win[T][4], uu[T][4], Ar[U], Br[U];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            win[t][j] = 0.0f;
+            uu[t][j] = 0.0f;
+        }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        Ar[j] = 0.0f;
+        Br[j] = 0.0f;
+    }
+    // the ring slots read before they are first written belong to the invalid cone; zero them so that no
+    // NaN/Inf garbage is ever combined (finite garbage is harmless: it never reaches a stored value)
+    for (int i = tid; i < T * 4 * BW + 8; i += BW)
+        smem_raw[i] = 0.0f;
+
+    // HBM latency (~1-2 us under load) is several steps long: keep PF rows in flight per thread with cp.async
+    // into the staging ring; rows (or columns) outside the image are zero-filled (src-size 0)
+    const unsigned stage_base = static_cast<unsigned>(__cvta_generic_to_shared(stage + tid));
+    auto prefetch = [&](int y, int slot) {
+        const bool ok = col_ok && y >= 0 && y < H;
+        const size_t idx = ok ? static_cast<size_t>(y) * L + colofs : 0;
+        const unsigned n = ok ? 4u : 0u;
+        const unsigned d = stage_base + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(o_src + idx), "r"(n) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + BW * 4), "l"(u_src + idx), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 2 * BW * 4), "l"(coefA + idx), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 3 * BW * 4), "l"(coefB + idx), "r"(n)
+                     : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int j = 0; j < PF; ++j)
+        prefetch(r0 - T + j, j);   // rows of steps 0 .. PF-1
+    __syncthreads();
+
+    for (int base = 0; base < nsteps; base += U) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int s = base + k;
+            if (s < nsteps) {  // uniform across the CTA
+                const int y_in = r0 - T + s;
+                // levels T..1 (level T first: it reads the coefficient slot the arrival below overwrites)
+#pragma unroll
+                for (int t = T; t >= 1; --t) {
+                    const int rho = y_in - 2 * t;
+                    const float c = win[t - 1][(k + 2) & 3];   // produced at step s-2
+                    float up = win[t - 1][(k + 1) & 3];        // s-3
+                    float dn = win[t - 1][(k + 3) & 3];        // s-1
+                    const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * BW + tid;
+                    float lf = row[-3];
+                    float rt = row[3];
+                    rt = m_r ? rt : 0.0f;
+                    lf = m_l ? lf : 0.0f;
+                    dn = (rho + 1) < (H - 1) ? dn : 0.0f;      // (:227)
+                    up = rho >= 1 ? up : 0.0f;                 // (:232)
+                    const float Ssum = ((rt + lf) + dn) + up;
+                    const float a = Ar[(k + U - 2 * t) % U];
+                    const float b = Br[(k + U - 2 * t) % U];
+                    const float uo = uu[t - 1][(k + 2) & 3];
+                    const float un = __fmaf_rn(step, Ssum, __fmaf_rn(a, c, b));
+                    const float on = __fmaf_rn(mom, uo, c + un);
+                    if (t < T) {
+                        win[t % T][k & 3] = on;   // (t % T only silences the bounds warning for t == T)
+                        uu[t % T][k & 3] = un;
+                        sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
+                    } else if (store_col && rho >= r0 && rho < r1) {
+                        const size_t idx = static_cast<size_t>(rho) * L + colofs;
+                        o_dst[idx] = on;
+                        u_dst[idx] = un;
+                    }
+                }
+                // level 0 arrives: the row of step s was requested PF steps ago; at most PF-1 younger groups
+                // may still be in flight
+                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+                {
+                    const float* st = stage + (k % PF) * 4 * BW + tid;
+                    const float n_o = st[0];
+                    win[0][k & 3] = n_o;
+                    uu[0][k & 3] = st[BW];
+                    sm[(k & 3) * BW + tid] = n_o;
+                    Ar[k % U] = st[2 * BW];
+                    Br[k % U] = st[3 * BW];
+                }
+                prefetch(y_in + PF, k % PF);   // refill the slot just consumed (same thread: program order)
+                __syncthreads();
+            }
+        }
+    }
+}
+
+template <int T>
+static int launch_stream(const float* coefA, const float* coefB, const float* u_src, float* u_dst,
+    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+{
+    constexpr int S = kStreamThreads - 6 * T;
+    const int L = 3 * W;
+    const int nb = (L + S - 1) / S;
+    // chunks: fill the SMs (1 CTA per SM) with as few, as tall chunks as possible
+    const int sms = sm_count();
+    int nc = (sms + nb - 1) / nb;
+    if (nc < 1) nc = 1;
+    const int min_rows = 4 * T;  // below this the 3T-step pipeline fill dominates
+    if (nc > (H + min_rows - 1) / min_rows) nc = (H + min_rows - 1) / min_rows;
+    if (nc < 1) nc = 1;
+    const int chunk_rows = (H + nc - 1) / nc;
+    nc = (H + chunk_rows - 1) / chunk_rows;
+    const size_t smem = (static_cast<size_t>(T) * 4 * kStreamThreads + 8 + kStreamPrefetch * 4 * kStreamThreads) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(smem));
+        if (e != cudaSuccess)
+            return static_cast<int>(e);
+        configured = true;
+    }
+    const dim3 grid(nb, nc);
+    solver_stream_kernel<T><<<grid, kStreamThreads, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H,
+        chunk_rows, step, mom);
+    count_launch();
+    return launch_status();
+}
+
+// T in {8, 4}; returns VSC_E_INVALID for any other value (callers fall back to unblocked sweeps)
+int solver_stream_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
+    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+{
+    if (T == 8)
+        return launch_stream<8>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    if (T == 4)
+        return launch_stream<4>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    return VSC_E_INVALID;
+}
+
+}  // namespace vsc
