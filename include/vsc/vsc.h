@@ -79,6 +79,10 @@ VSC_API uint64_t vsc_launch_count(void);
 VSC_API int vsc_correlation_f32(const float* in1, const float* in2, float* out, int N, int C, int H, int W,
     int max_displacement, int legacy, vsc_stream_t stream);
 
+/* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases), plain loads
+ * otherwise;  1: always the plain-load stager.  Same arithmetic, same results.  For tests. */
+VSC_API int vsc_set_correlation_mode(int mode);
+
 /* custom::Warp: masked bilinear backward warp (warp.cc:71-134 / warp_cuda.cu:29-84).
  * in [N,C,H,W], flow [N,2,H,W] (pixels), out [N,C,H,W]; out = 0 where the bilinear validity
  * mask is <= 0.999. */

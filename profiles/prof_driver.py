@@ -29,7 +29,7 @@ for (W, H) in ((3840, 2160), (1920, 1080)):
     if "solver" in which:
         pr, tg, wt = rnd(H, W, 3), rnd(H, W, 3), rnd(H, W, 3) * 2
         out = pr.clone()
-        V.get_consist_out(pr, tg, wt, 6, 0.15, 0.15, out)
+        V.get_consist_out(pr, tg, wt, 16, 0.15, 0.15, out)
         torch.cuda.synchronize()
     if "stage_a" in which:
         ims = [rnd(H, W, 3) for _ in range(7)]

@@ -171,3 +171,24 @@ def test_ops_reject_bad_arguments(V, dev):
     with pytest.raises(V.VscError):
         V.warp(a.cpu(), torch.zeros((1, 2, 4, 4)))  # no CPU fallback
     assert V.lib().vsc_correlation_f32(None, None, None, 1, 1, 1, 1, 4, 0, None) == -1
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 8, 32), (2, 12, 16, 20), (1, 196, 36, 60), (1, 64, 72, 120), (1, 5, 9, 44),
+                                   (1, 32, 136, 240)])
+@pytest.mark.parametrize("legacy", [False, True])
+def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, legacy):
+    """W % 4 == 0: the TMA-staged kernel (default) and the plain-load stager run the same contraction."""
+    N, C, H, W = shape
+    a, b = cu(synth.features(N, C, H, W, 21), dev), cu(synth.features(N, C, H, W, 22), dev)
+    L = V.lib()
+    try:
+        assert L.vsc_set_correlation_mode(1) == 0
+        plain = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(0) == 0
+        tma = V.correlation(a, b, legacy=legacy)
+        tma2 = V.correlation(a, b, legacy=legacy)  # twice on the same stream (reference test.py:70-71)
+    finally:
+        L.vsc_set_correlation_mode(0)
+    torch.cuda.synchronize()
+    assert torch.equal(tma, plain)
+    assert torch.equal(tma, tma2)

@@ -9,16 +9,22 @@
 // call, then runs one 32-thread block per output pixel with 81 barriers.  Here the contraction
 // reads NCHW directly, with no scratch memory and no allocation:
 //   * a CTA owns a 32x8 tile of output pixels for all 81 displacements;
-//   * per chunk of KC channels it stages the in1 tile and the in2 tile + 4-pixel halo in shared
-//     memory (zero-filled outside the image, which implements the zero padding);
-//   * a thread owns 4 consecutive pixels x 9 horizontal x 3 vertical displacements = 108 fp32
-//     accumulators in registers and walks the channels in order with explicit FMAs, so every
-//     shared-memory word it loads (128-bit LDS) feeds ~2.7 FMAs and each output value is the same
-//     sequential-over-c fp32 sum the reference's CPU kernel forms;
-//   * results leave as 128-bit stores straight into the [N,9,9,H,W] layout (the legacy
-//     [N,81,H,W] layout is byte-identical; it only adds the 1/C scale).
-// Any max_displacement other than 4 takes a plain one-thread-per-output kernel (no shipped model
-// uses one; model_spec.py:161-162).
+//   * per chunk of KC=8 channels the in1 tile [8][8][32] and the in2 tile + 4-pixel halo [8][16][40]
+//     are staged in shared memory by TMA (cp.async.bulk.tensor, 4-D tensor maps over [N][C][H][W]).
+//     The out-of-bounds zero fill of TMA implements the op's zero padding (negative start
+//     coordinates at the image border, channels beyond C).  A dedicated producer warp keeps a
+//     3-stage full/empty mbarrier ring ahead of the six consumer warps;
+//   * a consumer thread owns 4 consecutive pixels x 9 horizontal x 3 vertical displacements = 108 fp32
+//     accumulators in registers and walks the channels in order with explicit FMAs: per channel 10
+//     128-bit LDS feed 108 FMAs, and every output value is the same sequential-over-c fp32 sum the
+//     reference's CPU kernel forms;
+//   * results leave as 128-bit streaming stores straight into the [N,9,9,H,W] layout (the legacy
+//     [N,81,H,W] layout is byte-identical; it only adds the division by C).
+// TMA needs 16-byte aligned row strides (W % 4 == 0) and base pointers; other shapes take the same
+// compute loop behind a plain-load stager.  Any max_displacement other than 4 takes a one-thread-
+// per-output kernel (no shipped model uses one; model_spec.py:161-162).
+#include <cuda.h>
+
 #include "vsc_common.cuh"
 
 namespace vsc {
@@ -26,81 +32,83 @@ namespace vsc {
 constexpr int kMD = 4;
 constexpr int kP = 2 * kMD + 1;           // 9
 constexpr int kTW = 32, kTH = 8;          // output tile
-constexpr int kBW = kTW + 2 * kMD;        // 40: in2 tile row (floats), 160 B = 16B-aligned rows
+constexpr int kBW = kTW + 2 * kMD;        // 40: in2 tile row (floats), 160 B
 constexpr int kBH = kTH + 2 * kMD;        // 16
-constexpr int kKC = 8;                    // channels per shared-memory stage
-constexpr int kCorrThreads = 192;         // 64 pixel-quads x 3 vertical-displacement groups
+constexpr int kKC = 8;                    // channels per stage
+constexpr int kConsumers = 192;           // 64 pixel-quads x 3 vertical-displacement groups (6 warps)
 constexpr int kASize = kTH * kTW;         // 256 floats per channel
 constexpr int kBSize = kBH * kBW;         // 640 floats per channel
+constexpr int kStages = 3;
+constexpr int kStageFloats = kKC * (kASize + kBSize);                 // 7168 floats = 28 KB
+constexpr unsigned kStageBytes = kStageFloats * sizeof(float);
 
-__global__ void __launch_bounds__(kCorrThreads) correlation_md4_kernel(const float* __restrict__ in1,
-    const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float divisor, int legacy, int vec_store)
+// ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) ------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-    __shared__ __align__(16) float sA[kKC * kASize];
-    __shared__ __align__(16) float sB[kKC * kBSize];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2,
+    int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
-    const int tid = threadIdx.x;
-    const int q = tid & 63;        // pixel quad inside the tile
-    const int g = tid >> 6;        // vertical displacement group: ph = 3g .. 3g+2 (warp-uniform)
-    const int r = q >> 3;          // tile row 0..7
-    const int qc = (q & 7) * 4;    // first tile column of the quad
-    const int w0 = blockIdx.x * kTW;
-    const int h0 = blockIdx.y * kTH;
-    const int n = blockIdx.z;
-    const size_t HW = static_cast<size_t>(H) * W;
-    const float* a_img = in1 + static_cast<size_t>(n) * C * HW;
-    const float* b_img = in2 + static_cast<size_t>(n) * C * HW;
-
-    float acc[3][kP][4];
+// ---- the contraction of one staged channel chunk (shared by both stagers) ---------------------------
+__device__ __forceinline__ void correlate_chunk(const float* __restrict__ sA, const float* __restrict__ sB, int r, int qc,
+    int g, float (&acc)[3][kP][4])
+{
+#pragma unroll 1
+    for (int c = 0; c < kKC; ++c) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&sA[c * kASize + r * kTW + qc]);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
+            const float* brow = &sB[c * kBSize + (r + 3 * g + i) * kBW + qc];
+            const float4 b0 = *reinterpret_cast<const float4*>(brow);
+            const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
+            const float4 b2 = *reinterpret_cast<const float4*>(brow + 8);
+            const float bv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-        for (int j = 0; j < kP; ++j)
+            for (int j = 0; j < kP; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                acc[i][j][k] = 0.0f;
-
-    for (int cbase = 0; cbase < C; cbase += kKC) {
-        const int kc = min(kKC, C - cbase);
-        __syncthreads();  // previous stage fully consumed
-        // in1 tile: kc x 8 x 32
-        for (int i = tid; i < kc * kASize; i += kCorrThreads) {
-            const int c = i / kASize, rem = i - c * kASize;
-            const int y = h0 + rem / kTW, x = w0 + (rem % kTW);
-            sA[i] = (y < H && x < W) ? __ldg(a_img + (cbase + c) * HW + static_cast<size_t>(y) * W + x) : 0.0f;
-        }
-        // in2 tile + halo: kc x 16 x 40
-        for (int i = tid; i < kc * kBSize; i += kCorrThreads) {
-            const int c = i / kBSize, rem = i - c * kBSize;
-            const int y = h0 - kMD + rem / kBW, x = w0 - kMD + (rem % kBW);
-            sB[i] = (y >= 0 && y < H && x >= 0 && x < W)
-                ? __ldg(b_img + (cbase + c) * HW + static_cast<size_t>(y) * W + x)
-                : 0.0f;
-        }
-        __syncthreads();
-        for (int c = 0; c < kc; ++c) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&sA[c * kASize + r * kTW + qc]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float* brow = &sB[c * kBSize + (r + 3 * g + i) * kBW + qc];
-                const float4 b0 = *reinterpret_cast<const float4*>(brow);
-                const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
-                const float4 b2 = *reinterpret_cast<const float4*>(brow + 8);
-                const float bv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-                for (int j = 0; j < kP; ++j)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        acc[i][j][k] = __fmaf_rn(av[k], bv[k + j], acc[i][j][k]);
-            }
+                for (int k = 0; k < 4; ++k)
+                    acc[i][j][k] = __fmaf_rn(av[k], bv[k + j], acc[i][j][k]);
         }
     }
+}
 
-    const int y = h0 + r;
-    const int x = w0 + qc;
+__device__ __forceinline__ void correlation_store(float* __restrict__ out, const float (&acc)[3][kP][4], int n, int g,
+    int y, int x, int H, int W, float divisor, int legacy, int vec_store)
+{
     if (y >= H || x >= W)
         return;
+    const size_t HW = static_cast<size_t>(H) * W;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int ph = 3 * g + i;
@@ -121,6 +129,135 @@ __global__ void __launch_bounds__(kCorrThreads) correlation_md4_kernel(const flo
             }
         }
     }
+}
+
+// ---- TMA-staged kernel: 6 consumer warps + 1 producer warp ------------------------------------------
+__global__ void __maxnreg__(144) correlation_md4_tma_kernel(
+    const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out, int C,
+    int H, int W, float divisor, int legacy, int vec_store)
+{
+    extern __shared__ __align__(128) unsigned char smem_bytes[];
+    float* stage_mem = reinterpret_cast<float*>(smem_bytes);
+    __shared__ __align__(8) unsigned long long bars[2 * kStages];  // full[0..2], empty[0..2]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int w0 = blockIdx.x * kTW;
+    const int h0 = blockIdx.y * kTH;
+    const int n = blockIdx.z;
+    const int nchunks = (C + kKC - 1) / kKC;
+    const unsigned bar0 = smem_u32(bars);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar0 + 8 * i, 1);                       // full: the producer's arrive.expect_tx
+            mbar_init(bar0 + 8 * (kStages + i), kConsumers / 32);  // empty: one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kConsumers / 32) {
+        // ===== producer warp: one elected lane drives TMA =====
+        if ((tid & 31) == 0) {
+            for (int j = 0; j < nchunks; ++j) {
+                const int s = j % kStages;
+                if (j >= kStages)
+                    mbar_wait(bar0 + 8 * (kStages + s), ((j / kStages) - 1) & 1);
+                const unsigned full = bar0 + 8 * s;
+                mbar_expect_tx(full, kStageBytes);
+                const unsigned dstA = smem_u32(stage_mem + s * kStageFloats);
+                const unsigned dstB = dstA + kKC * kASize * sizeof(float);
+                tma_load_4d(dstA, &mapA, full, w0, h0, j * kKC, n);
+                tma_load_4d(dstB, &mapB, full, w0 - kMD, h0 - kMD, j * kKC, n);
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int q = tid & 63;        // pixel quad inside the tile
+    const int g = tid >> 6;        // vertical displacement group: ph = 3g .. 3g+2 (warp-uniform)
+    const int r = q >> 3;          // tile row 0..7
+    const int qc = (q & 7) * 4;    // first tile column of the quad
+    float acc[3][kP][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < kP; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                acc[i][j][k] = 0.0f;
+
+    for (int j = 0; j < nchunks; ++j) {
+        const int s = j % kStages;
+        mbar_wait(bar0 + 8 * s, (j / kStages) & 1);
+        const float* sA = stage_mem + s * kStageFloats;
+        correlate_chunk(sA, sA + kKC * kASize, r, qc, g, acc);
+        __syncwarp();
+        if ((tid & 31) == 0)
+            mbar_arrive(bar0 + 8 * (kStages + s));
+    }
+    correlation_store(out, acc, n, g, h0 + r, w0 + qc, H, W, divisor, legacy, vec_store);
+}
+
+// ---- plain-load stager for shapes TMA cannot address (W % 4 != 0 or unaligned bases) ----------------
+__global__ void __launch_bounds__(kConsumers) correlation_md4_ld_kernel(const float* __restrict__ in1,
+    const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float divisor, int legacy,
+    int vec_store)
+{
+    __shared__ __align__(16) float sA[kKC * kASize];
+    __shared__ __align__(16) float sB[kKC * kBSize];
+    const int tid = threadIdx.x;
+    const int q = tid & 63, g = tid >> 6, r = q >> 3, qc = (q & 7) * 4;
+    const int w0 = blockIdx.x * kTW, h0 = blockIdx.y * kTH, n = blockIdx.z;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const float* a_img = in1 + static_cast<size_t>(n) * C * HW;
+    const float* b_img = in2 + static_cast<size_t>(n) * C * HW;
+    float acc[3][kP][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < kP; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                acc[i][j][k] = 0.0f;
+
+    constexpr int kNA = (kKC * kASize + kConsumers - 1) / kConsumers;  // 11 loads per thread
+    constexpr int kNB = (kKC * kBSize + kConsumers - 1) / kConsumers;  // 27
+    for (int cbase = 0; cbase < C; cbase += kKC) {
+        // issue every load of the stage before the first store: one memory round trip per stage
+        float va[kNA], vb[kNB];
+#pragma unroll
+        for (int j = 0; j < kNA; ++j) {
+            const int i = tid + j * kConsumers;
+            const int c = i / kASize, rem = i % kASize;
+            const int y = h0 + rem / kTW, x = w0 + rem % kTW;
+            const bool ok = i < kKC * kASize && cbase + c < C && y < H && x < W;
+            va[j] = ok ? __ldg(a_img + (cbase + c) * HW + static_cast<size_t>(y) * W + x) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+            const int i = tid + j * kConsumers;
+            const int c = i / kBSize, rem = i % kBSize;
+            const int y = h0 - kMD + rem / kBW, x = w0 - kMD + rem % kBW;
+            const bool ok = i < kKC * kBSize && cbase + c < C && y >= 0 && y < H && x >= 0 && x < W;
+            vb[j] = ok ? __ldg(b_img + (cbase + c) * HW + static_cast<size_t>(y) * W + x) : 0.0f;
+        }
+        __syncthreads();  // previous stage fully consumed
+#pragma unroll
+        for (int j = 0; j < kNA; ++j)
+            if (tid + j * kConsumers < kKC * kASize)
+                sA[tid + j * kConsumers] = va[j];
+#pragma unroll
+        for (int j = 0; j < kNB; ++j)
+            if (tid + j * kConsumers < kKC * kBSize)
+                sB[tid + j * kConsumers] = vb[j];
+        __syncthreads();
+        correlate_chunk(sA, sB, r, qc, g, acc);
+    }
+    correlation_store(out, acc, n, g, h0 + r, w0 + qc, H, W, divisor, legacy, vec_store);
 }
 
 // any max_displacement: one thread per output value, sequential fp32 sum over c
@@ -149,7 +286,57 @@ __global__ void __launch_bounds__(256) correlation_generic_kernel(const float* _
     out[static_cast<size_t>(n) * per_n + i] = use_div ? acc / scale : acc;
 }
 
+// ---- host side: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess
+            && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// [N][C][H][W] fp32, box [1][KC][bh][bw]; out-of-bounds elements read as zero
+static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int W, int bw, int bh)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(C),
+        static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 4, static_cast<cuuint64_t>(W) * H * 4,
+        static_cast<cuuint64_t>(W) * H * C * 4};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), kKC, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+        == CUDA_SUCCESS;
+}
+
+int g_corr_mode = 0;  // 0 auto, 1 force the plain-load stager (tests)
+
 }  // namespace vsc
+
+extern "C" int vsc_set_correlation_mode(int mode)
+{
+    if (mode < 0 || mode > 1)
+        return VSC_E_INVALID;
+    vsc::g_corr_mode = mode;
+    return VSC_OK;
+}
 
 extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* out, int N, int C, int H, int W,
     int max_displacement, int legacy, vsc_stream_t stream)
@@ -161,21 +348,41 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
         return VSC_E_INVALID;
     if (!aligned4(in1) || !aligned4(in2) || !aligned4(out))
         return VSC_E_ALIGN;
+    cudaStream_t st = as_stream(stream);
     if (max_displacement == kMD) {
         const int vec = (W % 4 == 0) && aligned16(out);
         const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), N);
         if (grid.y > 65535)
             return VSC_E_INVALID;
-        correlation_md4_kernel<<<grid, kCorrThreads, 0, as_stream(stream)>>>(in1, in2, out, C, H, W,
-            static_cast<float>(C), legacy ? 1 : 0, vec);
+        const float divisor = static_cast<float>(C);
+        const bool tma_ok = g_corr_mode == 0 && (W % 4 == 0) && aligned16(in1) && aligned16(in2);
+        if (tma_ok) {
+            CUtensorMap mapA, mapB;
+            if (make_map(&mapA, in1, N, C, H, W, kTW, kTH) && make_map(&mapB, in2, N, C, H, W, kBW, kBH)) {
+                constexpr size_t smem = kStages * kStageBytes;
+                static bool configured = false;
+                if (!configured) {
+                    const cudaError_t e = cudaFuncSetAttribute(correlation_md4_tma_kernel,
+                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                    if (e != cudaSuccess)
+                        return static_cast<int>(e);
+                    configured = true;
+                }
+                correlation_md4_tma_kernel<<<grid, kConsumers + 32, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
+                    legacy ? 1 : 0, vec);
+                count_launch();
+                return launch_status();
+            }
+        }
+        correlation_md4_ld_kernel<<<grid, kConsumers, 0, st>>>(in1, in2, out, C, H, W, divisor, legacy ? 1 : 0, vec);
         count_launch();
         return launch_status();
     }
     const int P = 2 * max_displacement + 1;
     const size_t per_n = static_cast<size_t>(P) * P * H * W;
     const dim3 grid(cdiv(static_cast<long long>(per_n), 256), N);
-    correlation_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(in1, in2, out, C, H, W, max_displacement,
-        static_cast<float>(C), legacy ? 1 : 0);
+    correlation_generic_kernel<<<grid, 256, 0, st>>>(in1, in2, out, C, H, W, max_displacement, static_cast<float>(C),
+        legacy ? 1 : 0);
     count_launch();
     return launch_status();
 }

@@ -4,11 +4,10 @@
 //
 // The reference launches one 32-thread block per 32 pixels PER CHANNEL, so the flow is re-read
 // and the sampling geometry + validity mask recomputed C times, with fp64 multiplies on every
-// tap.  Here a thread owns VEC consecutive pixels of one image row: it reads the flow once,
-// derives the four tap offsets / weights once (the mask decision in the reference's own
-// float/double sequence, so the `mask > 0.999` threshold falls identically), and then streams
-// over a chunk of channels doing only gathers + 4 fp32 multiply-adds per value, with 128-bit
-// flow loads and output stores when the row length allows.  HBM traffic = the algorithmic
+// tap.  Here a thread owns one pixel: it reads the flow once, derives the four tap offsets /
+// weights once (the mask decision in the reference's own float/double sequence, so the
+// `mask > 0.999` threshold falls identically), and then streams over a chunk of channels doing
+// only gathers + 4 fp32 multiply-adds per value.  HBM traffic = the algorithmic
 // 4*N*H*W*(2C+2) bytes (gathers hit L1/L2: neighbouring pixels sample neighbouring taps).
 #include "vsc_common.cuh"
 
@@ -81,52 +80,41 @@ __device__ __forceinline__ float warp_sample(const float* __restrict__ plane, co
     return v;
 }
 
-// grid: x = pixel groups of one image, y = channel chunk, z = n
-template <int VEC>
+// grid: x = 256-pixel groups of one image, y = channel chunk, z = n.  One pixel per thread: the 32 lanes of a
+// warp sample 32 neighbouring positions, so each of the four gathers touches a handful of 32-byte sectors and
+// the store is one full 128-byte line (a 4-pixels-per-thread variant with 128-bit stores was measured 4x
+// worse: its gathers stride 16 bytes between lanes, 29 sectors per request -- profiles/r1_notes.md).
+// The channel loop is unrolled 4x: 16 independent gathers in flight per thread.
 __global__ void __launch_bounds__(256) warp_nchw_kernel(const float* __restrict__ in, const float* __restrict__ flow,
     float* __restrict__ out, int C, int H, int W, int chunk)
 {
     const int HW = H * W;
-    const int groups = HW / VEC;  // VEC==4 only when W % 4 == 0
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= groups)
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW)
         return;
     const int n = blockIdx.z;
     const int c0 = blockIdx.y * chunk;
     const int c1 = min(C, c0 + chunk);
-    const int p = g * VEC;
     const int y = p / W;
     const int x = p - y * W;
-
-    const float* fu = flow + (static_cast<size_t>(n) * 2 + 0) * HW + p;
-    const float* fv = flow + (static_cast<size_t>(n) * 2 + 1) * HW + p;
-    WarpTap t[VEC];
-    if constexpr (VEC == 4) {
-        const float4 u4 = ldg_stream4(fu);
-        const float4 v4 = ldg_stream4(fv);
-        t[0] = warp_setup(x + 0, y, u4.x, v4.x, W, H);
-        t[1] = warp_setup(x + 1, y, u4.y, v4.y, W, H);
-        t[2] = warp_setup(x + 2, y, u4.z, v4.z, W, H);
-        t[3] = warp_setup(x + 3, y, u4.w, v4.w, W, H);
-    } else {
-        t[0] = warp_setup(x, y, ldg_stream(fu), ldg_stream(fv), W, H);
-    }
+    const float* fl = flow + static_cast<size_t>(n) * 2 * HW + p;
+    const WarpTap t = warp_setup(x, y, ldg_stream(fl), ldg_stream(fl + HW), W, H);
 
     const float* ip = in + (static_cast<size_t>(n) * C + c0) * HW;
     float* op = out + (static_cast<size_t>(n) * C + c0) * HW + p;
-#pragma unroll 2
-    for (int c = c0; c < c1; ++c, ip += HW, op += HW) {
-        if constexpr (VEC == 4) {
-            float4 r;
-            r.x = warp_sample(ip, t[0]);
-            r.y = warp_sample(ip, t[1]);
-            r.z = warp_sample(ip, t[2]);
-            r.w = warp_sample(ip, t[3]);
-            stg_stream4(op, r);
-        } else {
-            *op = warp_sample(ip, t[0]);
-        }
+    int c = c0;
+    for (; c + 4 <= c1; c += 4, ip += 4 * static_cast<size_t>(HW), op += 4 * static_cast<size_t>(HW)) {
+        const float v0 = warp_sample(ip, t);
+        const float v1 = warp_sample(ip + HW, t);
+        const float v2 = warp_sample(ip + 2 * static_cast<size_t>(HW), t);
+        const float v3 = warp_sample(ip + 3 * static_cast<size_t>(HW), t);
+        __stcs(op, v0);
+        __stcs(op + HW, v1);
+        __stcs(op + 2 * static_cast<size_t>(HW), v2);
+        __stcs(op + 3 * static_cast<size_t>(HW), v3);
     }
+    for (; c < c1; ++c, ip += HW, op += HW)
+        __stcs(op, warp_sample(ip, t));
 }
 
 }  // namespace vsc
@@ -141,23 +129,18 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
         return VSC_E_INVALID;
     if (!aligned4(in) || !aligned4(flow) || !aligned4(out))
         return VSC_E_ALIGN;
-    const bool vec = (W % 4 == 0) && aligned16(flow) && aligned16(out);
-    const int VEC = vec ? 4 : 1;
-    const int groups = H * W / VEC;
-    const unsigned gx = cdiv(groups, 256);
-    // enough blocks for >= 4 waves of 148 SMs x 8 resident CTAs when the tensor allows, chunks of >= 4 channels
+    const unsigned gx = cdiv(static_cast<long long>(H) * W, 256);
+    // enough blocks for >= 4 waves of 148 SMs x 8 resident CTAs when the tensor allows, chunks of >= 8 channels
     const long long want = 4LL * sm_count() * 8;
     int nchunk = static_cast<int>((want + static_cast<long long>(gx) * N - 1) / (static_cast<long long>(gx) * N));
     if (nchunk < 1) nchunk = 1;
-    if (nchunk > (C + 3) / 4) nchunk = (C + 3) / 4;
+    if (nchunk > (C + 7) / 8) nchunk = (C + 7) / 8;
     if (nchunk > 65535) nchunk = 65535;
-    const int chunk = (C + nchunk - 1) / nchunk;
+    int chunk = (C + nchunk - 1) / nchunk;
+    chunk = (chunk + 3) / 4 * 4;  // whole unrolled groups
     nchunk = (C + chunk - 1) / chunk;
     const dim3 grid(gx, nchunk, N);
-    if (vec)
-        warp_nchw_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk);
-    else
-        warp_nchw_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk);
+    warp_nchw_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk);
     count_launch();
     return launch_status();
 }

@@ -165,8 +165,9 @@ static int launch_stream(const float* coefA, const float* coefB, const float* u_
     const int L = 3 * W;
     const int nb = (L + S - 1) / S;
     // chunks: fill the SMs (1 CTA per SM) with as few, as tall chunks as possible
+    // ONE wave: with 1 CTA per SM a grid of sms+1 CTAs takes twice as long as a grid of sms CTAs
     const int sms = sm_count();
-    int nc = (sms + nb - 1) / nb;
+    int nc = sms / nb;
     if (nc < 1) nc = 1;
     const int min_rows = 4 * T;  // below this the 3T-step pipeline fill dominates
     if (nc > (H + min_rows - 1) / min_rows) nc = (H + min_rows - 1) / min_rows;

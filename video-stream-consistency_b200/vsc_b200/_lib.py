@@ -23,6 +23,7 @@ PROTOTYPES = {
     "vsc_error_string": (C.c_char_p, [_i]),
     "vsc_launch_count": (C.c_uint64, []),
     "vsc_correlation_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "vsc_set_correlation_mode": (_i, [_i]),
     "vsc_warp_nchw_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "vsc_warp_hwc3": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "vsc_adap_comb": (_i, [_p] * 9 + [_f, _i, _i, _p]),
