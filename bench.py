@@ -138,7 +138,7 @@ def make_op_tensors(wl, dev):
                  torch.from_numpy(synth.features(1, C, h, w, 10 * d + i + 5)).to(dev),
                  torch.empty((1, 9, 9, h, w), device=dev)) for i, (C, h, w) in enumerate(wl["corr"])]
         warp = [(torch.from_numpy(synth.features(1, C, h, w, 20 * d + i)).to(dev),
-                 torch.from_numpy(synth.op_flow(1, h, w, 30 * d + i)).to(dev),
+                 torch.from_numpy(synth.op_flow_smooth(1, h, w, 30 * d + i)).to(dev),
                  torch.empty((1, C, h, w), device=dev)) for i, (C, h, w) in enumerate(wl["warp"])]
         sets.append((corr, warp))
     return sets

@@ -13,6 +13,7 @@ for p in (os.path.join(ROOT, "video-stream-consistency_b200"), ROOT, os.path.joi
 
 import torch  # noqa: E402
 
+import synth  # noqa: E402
 import vsc_b200 as V  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -58,7 +59,7 @@ if "corr" in which:
 if "warp" in which:
     for (C, h, w) in ((32, 544, 960), (64, 272, 480), (96, 136, 240), (64, 72, 120)):
         x = rnd(1, C, h, w)
-        f = (rnd(1, 2, h, w) - 0.5) * 8
+        f = torch.from_numpy(synth.op_flow_smooth(1, h, w, 3)).to(dev)
         for _ in range(2):
             V.warp(x, f)
         torch.cuda.synchronize()

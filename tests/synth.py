@@ -85,3 +85,17 @@ LIGHT_1080P_CORR = [(196, 9, 15), (128, 18, 30), (96, 36, 60), (64, 72, 120)]
 LIGHT_1080P_WARP = [(128, 18, 30), (96, 36, 60), (64, 72, 120)]
 DENSE_4K_CORR = [(196, 34, 60), (128, 68, 120), (96, 136, 240), (64, 272, 480), (32, 544, 960)]
 DENSE_4K_WARP = [(128, 68, 120), (96, 136, 240), (64, 272, 480), (32, 544, 960)]
+
+
+def op_flow_smooth(N: int, H: int, W: int, seed: int, amp: float = 2.0, noise: float = 0.25):
+    """a spatially smooth flow field (what a PWC-Net decoder level actually feeds custom::Warp): a global
+    translation + low-frequency sinusoids of amplitude `amp` px + N(0, noise) per pixel."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:H, 0:W].astype(np.float32)
+    f = np.empty((N, 2, H, W), np.float32)
+    for n in range(N):
+        tx, ty = rng.uniform(-amp, amp, 2)
+        f[n, 0] = tx + amp * np.sin(2 * np.pi * (x / max(W, 1) + 0.5 * y / max(H, 1)) + n)
+        f[n, 1] = ty + amp * np.cos(2 * np.pi * (y / max(H, 1) - 0.3 * x / max(W, 1)) + n)
+    f += rng.normal(0, noise, f.shape).astype(np.float32)
+    return f

@@ -90,15 +90,24 @@ __device__ __forceinline__ void correlate_chunk(const float* __restrict__ sA, co
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const float* brow = &sB[c * kBSize + (r + 3 * g + i) * kBW + qc];
-            const float4 b0 = *reinterpret_cast<const float4*>(brow);
-            const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
-            const float4 b2 = *reinterpret_cast<const float4*>(brow + 8);
-            const float bv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+            // the 12 in2 values of the row are consumed one 128-bit load at a time (value m feeds the
+            // accumulators (j = m - k, k)), so only 4 of them are live: keeps the kernel at <= 128 registers,
+            // i.e. two CTAs per SM
 #pragma unroll
-            for (int j = 0; j < kP; ++j)
+            for (int h = 0; h < 3; ++h) {
+                const float4 b4 = *reinterpret_cast<const float4*>(brow + 4 * h);
+                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    acc[i][j][k] = __fmaf_rn(av[k], bv[k + j], acc[i][j][k]);
+                for (int mm = 0; mm < 4; ++mm) {
+                    const int m = 4 * h + mm;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = m - k;
+                        if (j >= 0 && j < kP)
+                            acc[i][j][k] = __fmaf_rn(av[k], bv[mm], acc[i][j][k]);
+                    }
+                }
+            }
         }
     }
 }
@@ -132,7 +141,7 @@ __device__ __forceinline__ void correlation_store(float* __restrict__ out, const
 }
 
 // ---- TMA-staged kernel: 6 consumer warps + 1 producer warp ------------------------------------------
-__global__ void __maxnreg__(144) correlation_md4_tma_kernel(
+__global__ void __maxnreg__(128) correlation_md4_tma_kernel(
     const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out, int C,
     int H, int W, float divisor, int legacy, int vec_store)
 {
@@ -362,8 +371,11 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
                 constexpr size_t smem = kStages * kStageBytes;
                 static bool configured = false;
                 if (!configured) {
-                    const cudaError_t e = cudaFuncSetAttribute(correlation_md4_tma_kernel,
+                    cudaError_t e = cudaFuncSetAttribute(correlation_md4_tma_kernel,
                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                    if (e == cudaSuccess)  // two 84 KB CTAs per SM need the large shared-memory carve-out
+                        e = cudaFuncSetAttribute(correlation_md4_tma_kernel,
+                            cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                     if (e != cudaSuccess)
                         return static_cast<int>(e);
                     configured = true;

@@ -26,6 +26,8 @@
 //
 // Rings are indexed by (step mod 4) / (step mod 2T); the step loop is unrolled 2T times so every ring index
 // is a compile-time constant and the rings live in registers without moves.
+#include <type_traits>
+
 #include "vsc_common.cuh"
 
 namespace vsc {
@@ -57,8 +59,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const 
     const int r1 = min(H, r0 + chunk_rows);
     const bool col_ok = gi >= 0 && gi < L;
     const bool store_col = col_ok && tid >= 3 * T && tid < 3 * T + S;
-    const bool m_r = gi < 3 * (W - 2);  // right neighbour included  <=>  x+1 < W-1   (flowconsistency.cu:215)
-    const bool m_l = gi >= 3;           // left neighbour included   <=>  x-1 >= 0    (:221)
+    // publishes to the neighbour-exchange ring: image columns except the last pixel column (see step_body)
+    const bool pub_ok = col_ok && gi < 3 * (W - 1);
     const int nsteps = (r1 - r0) + 3 * T;
     const size_t colofs = static_cast<size_t>(col_ok ? gi : 0);
 
@@ -102,56 +104,73 @@ __global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const 
         prefetch(r0 - T + j, j);   // rows of steps 0 .. PF-1
     __syncthreads();
 
+    // One step of the pipeline.  ROWMASK selects the variant that applies the reference's top/bottom inclusion
+    // tests (flowconsistency.cu:227,232); it is needed only while some level works on rows <= 0 or >= H-2, a
+    // CTA-uniform condition true for a handful of steps of the first and last row chunk.
+    // The left/right tests (:215,:221) cost nothing: a column outside the image, and the last pixel column
+    // (never a valid right neighbour: x+1 < W-1), simply never PUBLISH to the shared ring, whose slots were
+    // zeroed above -- so their readers add 0.0f, which is exactly the excluded term.
+    auto step_body = [&](auto rowmask_tag, const int k, const int y_in) {
+        constexpr bool ROWMASK = decltype(rowmask_tag)::value;
+        // levels T..1 (level T first: it reads the coefficient slot the arrival below overwrites)
+#pragma unroll
+        for (int t = T; t >= 1; --t) {
+            const int rho = y_in - 2 * t;
+            const float c = win[t - 1][(k + 2) & 3];   // produced at step s-2
+            float up = win[t - 1][(k + 1) & 3];        // s-3
+            float dn = win[t - 1][(k + 3) & 3];        // s-1
+            const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * BW + tid;
+            const float lf = row[-3];
+            const float rt = row[3];
+            if constexpr (ROWMASK) {
+                dn = (rho + 1) < (H - 1) ? dn : 0.0f;  // (:227)
+                up = rho >= 1 ? up : 0.0f;             // (:232)
+            }
+            const float Ssum = ((rt + lf) + dn) + up;
+            const float a = Ar[(k + U - 2 * t) % U];
+            const float b = Br[(k + U - 2 * t) % U];
+            const float uo = uu[t - 1][(k + 2) & 3];
+            const float un = __fmaf_rn(step, Ssum, __fmaf_rn(a, c, b));
+            const float on = __fmaf_rn(mom, uo, c + un);
+            if (t < T) {
+                win[t % T][k & 3] = on;   // (t % T only silences the bounds warning for t == T)
+                uu[t % T][k & 3] = un;
+                if (pub_ok)
+                    sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
+            } else if (store_col && rho >= r0 && rho < r1) {
+                const size_t idx = static_cast<size_t>(rho) * L + colofs;
+                o_dst[idx] = on;
+                u_dst[idx] = un;
+            }
+        }
+        // level 0 arrives: the row of step s was requested PF steps ago; at most PF-1 younger groups may
+        // still be in flight
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+        {
+            const float* st = stage + (k % PF) * 4 * BW + tid;
+            const float n_o = st[0];
+            win[0][k & 3] = n_o;
+            uu[0][k & 3] = st[BW];
+            if (pub_ok)
+                sm[(k & 3) * BW + tid] = n_o;
+            Ar[k % U] = st[2 * BW];
+            Br[k % U] = st[3 * BW];
+        }
+        prefetch(y_in + PF, k % PF);   // refill the slot just consumed (same thread: program order)
+        __syncthreads();
+    };
+
     for (int base = 0; base < nsteps; base += U) {
 #pragma unroll
         for (int k = 0; k < U; ++k) {
             const int s = base + k;
             if (s < nsteps) {  // uniform across the CTA
                 const int y_in = r0 - T + s;
-                // levels T..1 (level T first: it reads the coefficient slot the arrival below overwrites)
-#pragma unroll
-                for (int t = T; t >= 1; --t) {
-                    const int rho = y_in - 2 * t;
-                    const float c = win[t - 1][(k + 2) & 3];   // produced at step s-2
-                    float up = win[t - 1][(k + 1) & 3];        // s-3
-                    float dn = win[t - 1][(k + 3) & 3];        // s-1
-                    const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * BW + tid;
-                    float lf = row[-3];
-                    float rt = row[3];
-                    rt = m_r ? rt : 0.0f;
-                    lf = m_l ? lf : 0.0f;
-                    dn = (rho + 1) < (H - 1) ? dn : 0.0f;      // (:227)
-                    up = rho >= 1 ? up : 0.0f;                 // (:232)
-                    const float Ssum = ((rt + lf) + dn) + up;
-                    const float a = Ar[(k + U - 2 * t) % U];
-                    const float b = Br[(k + U - 2 * t) % U];
-                    const float uo = uu[t - 1][(k + 2) & 3];
-                    const float un = __fmaf_rn(step, Ssum, __fmaf_rn(a, c, b));
-                    const float on = __fmaf_rn(mom, uo, c + un);
-                    if (t < T) {
-                        win[t % T][k & 3] = on;   // (t % T only silences the bounds warning for t == T)
-                        uu[t % T][k & 3] = un;
-                        sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
-                    } else if (store_col && rho >= r0 && rho < r1) {
-                        const size_t idx = static_cast<size_t>(rho) * L + colofs;
-                        o_dst[idx] = on;
-                        u_dst[idx] = un;
-                    }
-                }
-                // level 0 arrives: the row of step s was requested PF steps ago; at most PF-1 younger groups
-                // may still be in flight
-                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
-                {
-                    const float* st = stage + (k % PF) * 4 * BW + tid;
-                    const float n_o = st[0];
-                    win[0][k & 3] = n_o;
-                    uu[0][k & 3] = st[BW];
-                    sm[(k & 3) * BW + tid] = n_o;
-                    Ar[k % U] = st[2 * BW];
-                    Br[k % U] = st[3 * BW];
-                }
-                prefetch(y_in + PF, k % PF);   // refill the slot just consumed (same thread: program order)
-                __syncthreads();
+                // rows handled this step: y_in-2T .. y_in-2
+                if (y_in <= 2 * T || y_in >= H)
+                    step_body(std::true_type{}, k, y_in);
+                else
+                    step_body(std::false_type{}, k, y_in);
             }
         }
     }
