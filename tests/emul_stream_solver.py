@@ -7,7 +7,8 @@ Scheme: a CTA owns a band of BW consecutive floats of the flattened rows (row le
 At step s the level-0 row y_in = r0-T+s arrives, and level t (1..T) computes its row y_in-2t from level t-1
 rows (y_in-2t-1, y_in-2t, y_in-2t+1), which level t-1 produced at steps s-3, s-2, s-1 (skew 2 => all T levels
 of a step are independent).  Left/right neighbours come from a shared ring written at step s-2.
-Level T rows inside [r0,r1) x [g0+3T, g0+3T+S) are stored.  One barrier per step.
+Level T rows inside [r0,r1) x [g0+3T, g0+3T+S) are stored.  The skew also leaves one step of slack in the
+shared ring, so ONE barrier per TWO steps is enough (sync_every=2; with 3 the emulation diverges).
 """
 import numpy as np
 
@@ -38,7 +39,7 @@ def jacobi(out, u, A, B, W, H, step, mom, sweeps):
     return out, u
 
 
-def cta(out_src, u_src, A, B, out_dst, u_dst, W, H, step, mom, T, BW, g0, r0, r1):
+def cta(out_src, u_src, A, B, out_dst, u_dst, W, H, step, mom, T, BW, g0, r0, r1, sync_every=1):
     L = 3 * W
     S = BW - 6 * T
     tid = np.arange(BW)
@@ -50,7 +51,9 @@ def cta(out_src, u_src, A, B, out_dst, u_dst, W, H, step, mom, T, BW, g0, r0, r1
     uu = np.zeros((T, 4, BW), np.float32)
     Ar = np.zeros((2 * T, BW), np.float32)   # arrival ring, 2T slots
     Br = np.zeros((2 * T, BW), np.float32)
-    sm = np.zeros((T, 4, BW), np.float32)    # shared exchange ring
+    sm = np.zeros((T, 4, BW), np.float32)    # shared exchange ring as VISIBLE to other threads
+    sm_w = np.zeros((T, 4, BW), np.float32)  # writes since the last barrier (worst case: invisible until then)
+    pub_ok = col_ok & (gi < 3 * (W - 1))     # columns that publish (see the kernel: masks are free this way)
     nsteps = (r1 - r0) + 3 * T
     for s in range(nsteps):
         y_in = r0 - T + s
@@ -64,8 +67,6 @@ def cta(out_src, u_src, A, B, out_dst, u_dst, W, H, step, mom, T, BW, g0, r0, r1
             rt = np.zeros(BW, np.float32)
             lf[3:] = row[:-3]
             rt[:-3] = row[3:]
-            rt = np.where(gi < 3 * (W - 2), rt, f(0))
-            lf = np.where(gi >= 3, lf, f(0))
             dn = dn if (rho + 1) < (H - 1) else np.zeros(BW, np.float32)
             up = up if rho >= 1 else np.zeros(BW, np.float32)
             Ssum = ((rt + lf) + dn) + up
@@ -77,7 +78,7 @@ def cta(out_src, u_src, A, B, out_dst, u_dst, W, H, step, mom, T, BW, g0, r0, r1
             if t < T:
                 win[t][s & 3] = on
                 uu[t][s & 3] = un
-                sm[t][s & 3] = on
+                sm_w[t][s & 3] = np.where(pub_ok, on, f(0))
             else:
                 if r0 <= rho < r1:
                     ok = (tid >= 3 * T) & (tid < 3 * T + S) & col_ok
@@ -93,13 +94,14 @@ def cta(out_src, u_src, A, B, out_dst, u_dst, W, H, step, mom, T, BW, g0, r0, r1
             o0 = u0 = a0 = b0 = np.zeros(BW, np.float32)
         win[0][s & 3] = o0
         uu[0][s & 3] = u0
-        sm[0][s & 3] = o0
+        sm_w[0][s & 3] = np.where(pub_ok, o0, f(0))
         Ar[s % (2 * T)] = a0
         Br[s % (2 * T)] = b0
-        # __syncthreads()
+        if (s % sync_every) == sync_every - 1:   # __syncthreads(): everything written so far becomes visible
+            sm[:] = sm_w
 
 
-def stream_pass(out, u, A, B, W, H, step, mom, T, BW, nchunks):
+def stream_pass(out, u, A, B, W, H, step, mom, T, BW, nchunks, sync_every=1):
     L = 3 * W
     S = BW - 6 * T
     assert S > 0
@@ -112,5 +114,5 @@ def stream_pass(out, u, A, B, W, H, step, mom, T, BW, nchunks):
             r0, r1 = c * CH, min(H, (c + 1) * CH)
             if r0 >= r1:
                 continue
-            cta(out, u, A, B, out_dst, u_dst, W, H, step, mom, T, BW, b * S - 3 * T, r0, r1)
+            cta(out, u, A, B, out_dst, u_dst, W, H, step, mom, T, BW, b * S - 3 * T, r0, r1, sync_every)
     return out_dst, u_dst

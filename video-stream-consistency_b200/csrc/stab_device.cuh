@@ -41,6 +41,18 @@ __device__ __forceinline__ void hwc_warp_sample3(const float* __restrict__ in, i
     }
 }
 
+// one channel of the same sample (value-per-thread kernels): identical expression, identical result
+__device__ __forceinline__ float hwc_warp_sample1(const float* __restrict__ in, int W, const WarpGeom& g, int c)
+{
+    const float* p0 = in + (static_cast<size_t>(g.iy) * W + g.ix) * 3 + c;
+    const float* p1 = p0 + static_cast<size_t>(W) * 3;
+    const float ofx = 1.0f - g.fx;
+    const float ofy = 1.0f - g.fy;
+    const float tmp_1 = __ldg(p0) * ofx + __ldg(p0 + 3) * g.fx;
+    const float tmp_2 = __ldg(p1) * ofx + __ldg(p1 + 3) * g.fx;
+    return tmp_1 * ofy + tmp_2 * g.fy;
+}
+
 // kernel_adap_comb for one value, flowconsistency.cu:131-164
 __device__ __forceinline__ void adap_comb_value(float ci, float cp, float pi, float pp, float ni, float np, float ls,
     float alpha, float& adp_in, float& adp_pr)

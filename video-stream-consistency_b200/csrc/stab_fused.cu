@@ -14,6 +14,11 @@
 
 namespace vsc {
 
+// One thread per VALUE (pixel, channel) of a row, not per pixel: the image is interleaved HWC, so consecutive
+// threads touch consecutive floats -- every gather tap, every input read and every output write of a warp is
+// one contiguous 128-byte request when the flow is locally smooth.  (The first version used one thread per
+// pixel: stride-3 scalar accesses, 25 sectors per request, LSU-bound at 2.6 TB/s -- profiles/r1_notes.md.)
+// The three threads of a pixel recompute its warp geometry (a dozen ALU ops; the flow loads are broadcasts).
 __global__ void __launch_bounds__(256) stage_a_kernel(const float* __restrict__ origPrev,
     const float* __restrict__ origCur, const float* __restrict__ origNext, const float* __restrict__ procPrev,
     const float* __restrict__ procCur, const float* __restrict__ procNext, const float* __restrict__ lastStab,
@@ -21,30 +26,29 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const float* __restrict__ 
     float gamma, float* __restrict__ adapCmbIn, float* __restrict__ adapCmbPr, float* __restrict__ consWt, int W,
     int H)
 {
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float index inside the row
     const int iy = blockIdx.y;
-    if (ix >= W)
+    if (i >= 3 * W)
         return;
+    const int ix = i / 3;
+    const int c = i - 3 * ix;
     const size_t p = static_cast<size_t>(iy) * W + ix;
-    const WarpGeom gb = hwc_warp_geom(ix, iy, ldg_stream(flowBwd + p * flowC), ldg_stream(flowBwd + p * flowC + 1), W, H);
-    const WarpGeom gf = hwc_warp_geom(ix, iy, ldg_stream(flowFwd + p * flowC), ldg_stream(flowFwd + p * flowC + 1), W, H);
-    float pi[3], pp[3], ls[3], ni[3], np[3];
-    hwc_warp_sample3(origPrev, W, gb, pi);   // prevWarpIn   (:182)
-    hwc_warp_sample3(procPrev, W, gb, pp);   // prevWarpPr   (:183)
-    hwc_warp_sample3(origNext, W, gf, ni);   // nextWarpIn   (:186)
-    hwc_warp_sample3(procNext, W, gf, np);   // nextWarpPr   (:187)
-    hwc_warp_sample3(lastStab, W, gb, ls);   // lastStabWarp (:190)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float ci = ldg_stream(origCur + p * 3 + c);
-        const float cp = ldg_stream(procCur + p * 3 + c);
-        float ai, ap;
-        adap_comb_value(ci, cp, pi[c], pp[c], ni[c], np[c], ls[c], alpha, ai, ap);
-        if (adapCmbIn)
-            adapCmbIn[p * 3 + c] = ai;
-        adapCmbPr[p * 3 + c] = ap;
-        consWt[p * 3 + c] = consist_wt_value(ci, ai, beta, gamma);
-    }
+    const size_t v = p * 3 + c;
+    const WarpGeom gb = hwc_warp_geom(ix, iy, __ldg(flowBwd + p * flowC), __ldg(flowBwd + p * flowC + 1), W, H);
+    const WarpGeom gf = hwc_warp_geom(ix, iy, __ldg(flowFwd + p * flowC), __ldg(flowFwd + p * flowC + 1), W, H);
+    const float pi = hwc_warp_sample1(origPrev, W, gb, c);   // prevWarpIn   (:182)
+    const float pp = hwc_warp_sample1(procPrev, W, gb, c);   // prevWarpPr   (:183)
+    const float ni = hwc_warp_sample1(origNext, W, gf, c);   // nextWarpIn   (:186)
+    const float np = hwc_warp_sample1(procNext, W, gf, c);   // nextWarpPr   (:187)
+    const float ls = hwc_warp_sample1(lastStab, W, gb, c);   // lastStabWarp (:190)
+    const float ci = ldg_stream(origCur + v);
+    const float cp = ldg_stream(procCur + v);
+    float ai, ap;
+    adap_comb_value(ci, cp, pi, pp, ni, np, ls, alpha, ai, ap);
+    if (adapCmbIn)
+        adapCmbIn[v] = ai;
+    adapCmbPr[v] = ap;
+    consWt[v] = consist_wt_value(ci, ai, beta, gamma);
 }
 
 }  // namespace vsc
@@ -58,7 +62,7 @@ extern "C" int vsc_stage_a_fused(const float* origPrev, const float* origCur, co
     if (!origPrev || !origCur || !origNext || !procPrev || !procCur || !procNext || !lastStab || !flowFwd || !flowBwd
         || !adapCmbPr || !consWt || W < 2 || H < 2 || H > 65535 || (flow_channels != 2 && flow_channels != 3))
         return VSC_E_INVALID;
-    const dim3 grid(cdiv(W, 256), H);
+    const dim3 grid(cdiv(3LL * W, 256), H);
     stage_a_kernel<<<grid, 256, 0, as_stream(stream)>>>(origPrev, origCur, origNext, procPrev, procCur, procNext,
         lastStab, flowFwd, flowBwd, flow_channels, alpha, beta, gamma, adapCmbIn, adapCmbPr, consWt, W, H);
     count_launch();

@@ -32,15 +32,14 @@
 
 namespace vsc {
 
-constexpr int kStreamThreads = 512;
 constexpr int kStreamPrefetch = 8;  // must divide the unroll factor 2T (T in {4, 8})
 
-template <int T>
-__global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const float* __restrict__ coefA,
+// BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best)
+template <int T, int BW>
+__global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
 {
-    constexpr int BW = kStreamThreads;
     constexpr int S = BW - 6 * T;   // columns stored per band
     constexpr int U = 2 * T;        // unroll: lcm(4, 2T) for T in {4, 8}
     static_assert(U % 4 == 0, "ring period");
@@ -143,9 +142,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const 
                 u_dst[idx] = un;
             }
         }
-        // level 0 arrives: the row of step s was requested PF steps ago; at most PF-1 younger groups may
-        // still be in flight
-        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+        // level 0 arrives: the row of step s was requested PF steps ago.  Waiting is done every second step
+        // for two rows at once: at an even step at most PF-2 younger groups may still be in flight
+        if ((k & 1) == 0)
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");
         {
             const float* st = stage + (k % PF) * 4 * BW + tid;
             const float n_o = st[0];
@@ -157,7 +157,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const 
             Br[k % U] = st[3 * BW];
         }
         prefetch(y_in + PF, k % PF);   // refill the slot just consumed (same thread: program order)
-        __syncthreads();
+        // ONE barrier per TWO steps: a step reads ring slots (s-2)&3 (and its partner (s-1)&3) and writes
+        // slot s&3 (partner (s+1)&3) -- disjoint, and what step s needs was published before the barrier
+        // that closed step s-1 (worst-case visibility checked in tests/emul_stream_solver.py, sync_every=2)
+        if ((k & 1) == 1)
+            __syncthreads();
     };
 
     for (int base = 0; base < nsteps; base += U) {
@@ -176,37 +180,71 @@ __global__ void __launch_bounds__(kStreamThreads, 1) solver_stream_kernel(const 
     }
 }
 
-template <int T>
-static int launch_stream(const float* coefA, const float* coefB, const float* u_src, float* u_dst,
-    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+struct StreamGeom {
+    int nb, nc, chunk_rows;
+    long long cost;
+};
+
+// grid of one band width: bands x row chunks, at most ONE wave (1 CTA per SM: a grid of sms+1 CTAs takes twice
+// as long as a grid of sms CTAs); cost ~ per-SM time = steps x warps
+static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
 {
-    constexpr int S = kStreamThreads - 6 * T;
-    const int L = 3 * W;
-    const int nb = (L + S - 1) / S;
-    // chunks: fill the SMs (1 CTA per SM) with as few, as tall chunks as possible
-    // ONE wave: with 1 CTA per SM a grid of sms+1 CTAs takes twice as long as a grid of sms CTAs
-    const int sms = sm_count();
-    int nc = sms / nb;
+    StreamGeom g;
+    const int S = BW - 6 * T;
+    g.nb = (L + S - 1) / S;
+    int nc = sms / g.nb;
     if (nc < 1) nc = 1;
     const int min_rows = 4 * T;  // below this the 3T-step pipeline fill dominates
     if (nc > (H + min_rows - 1) / min_rows) nc = (H + min_rows - 1) / min_rows;
     if (nc < 1) nc = 1;
-    const int chunk_rows = (H + nc - 1) / nc;
-    nc = (H + chunk_rows - 1) / chunk_rows;
-    const size_t smem = (static_cast<size_t>(T) * 4 * kStreamThreads + 8 + kStreamPrefetch * 4 * kStreamThreads) * sizeof(float);
+    g.chunk_rows = (H + nc - 1) / nc;
+    g.nc = (H + g.chunk_rows - 1) / g.chunk_rows;
+    const long long waves = (static_cast<long long>(g.nb) * g.nc + sms - 1) / sms;
+    g.cost = waves * (g.chunk_rows + 3 * T) * BW;
+    return g;
+}
+
+template <int T, int BW>
+static int launch_stream(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
+    float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+{
+    const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + kStreamPrefetch * 4 * BW) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            static_cast<int>(smem));
+        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T, BW>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess)
             return static_cast<int>(e);
         configured = true;
     }
-    const dim3 grid(nb, nc);
-    solver_stream_kernel<T><<<grid, kStreamThreads, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H,
-        chunk_rows, step, mom);
+    const dim3 grid(g.nb, g.nc);
+    solver_stream_kernel<T, BW><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
+        step, mom);
     count_launch();
     return launch_status();
+}
+
+template <int T>
+static int launch_stream_best(const float* coefA, const float* coefB, const float* u_src, float* u_dst,
+    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+{
+    const int L = 3 * W, sms = sm_count();
+    const int cands[4] = {512, 448, 384, 256};
+    int best = 0;
+    StreamGeom bg = stream_geom(T, cands[0], L, H, sms);
+    for (int i = 1; i < 4; ++i) {
+        const StreamGeom g = stream_geom(T, cands[i], L, H, sms);
+        if (g.cost < bg.cost) {
+            bg = g;
+            best = i;
+        }
+    }
+    switch (best) {
+        case 0: return launch_stream<T, 512>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        case 1: return launch_stream<T, 448>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        case 2: return launch_stream<T, 384>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        default: return launch_stream<T, 256>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    }
 }
 
 // T in {8, 4}; returns VSC_E_INVALID for any other value (callers fall back to unblocked sweeps)
@@ -214,9 +252,9 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     if (T == 8)
-        return launch_stream<8>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        return launch_stream_best<8>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (T == 4)
-        return launch_stream<4>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        return launch_stream_best<4>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     return VSC_E_INVALID;
 }
 
