@@ -34,8 +34,7 @@ for (W, H) in ((3840, 2160), (1920, 1080)):
         torch.cuda.synchronize()
     if "stage_a" in which:
         ims = [rnd(H, W, 3) for _ in range(7)]
-        ff = (rnd(H, W, 3) - 0.5) * 6
-        fb = (rnd(H, W, 3) - 0.5) * 6
+        ff, fb = (torch.from_numpy(x).to(dev) for x in synth.flows(W, H, 3))  # smooth, like real optical flow
         for _ in range(2):
             V.stage_a_fused(*ims, ff, fb, 6800.0, 6800.0, 2.0)
         torch.cuda.synchronize()

@@ -82,25 +82,40 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         smem_raw[i] = 0.0f;
 
     // HBM latency (~1-2 us under load) is several steps long: keep PF rows in flight per thread with cp.async
-    // into the staging ring; rows (or columns) outside the image are zero-filled (src-size 0)
+    // into the staging ring; rows (or columns) outside the image are zero-filled (src-size 0: the source is
+    // not read, so its address may lie outside the arrays).
+    // Addressing: ONE running per-thread byte offset `boff` = offset of (row y_in, column gi) in any of the
+    // images, advanced by one row per step; the prefetch (PF rows ahead) and store (2T rows behind) row shifts
+    // are folded into CTA-uniform base pointers, so forming an address is a 64-bit add.
     const unsigned stage_base = static_cast<unsigned>(__cvta_generic_to_shared(stage + tid));
-    auto prefetch = [&](int y, int slot) {
-        const bool ok = col_ok && y >= 0 && y < H;
-        const size_t idx = ok ? static_cast<size_t>(y) * L + colofs : 0;
-        const unsigned n = ok ? 4u : 0u;
+    const long long row_bytes = static_cast<long long>(L) * 4;
+    long long boff = (static_cast<long long>(r0 - T) * L + static_cast<long long>(colofs)) * 4;
+    auto copy_row = [&](const char* bo, const char* bu, const char* ba, const char* bb, long long off, int y,
+                        int slot) {
+        const unsigned n = (col_ok && y >= 0 && y < H) ? 4u : 0u;
         const unsigned d = stage_base + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(o_src + idx), "r"(n) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + BW * 4), "l"(u_src + idx), "r"(n)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(bo + off), "r"(n) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + BW * 4), "l"(bu + off), "r"(n) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 2 * BW * 4), "l"(ba + off), "r"(n)
                      : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 2 * BW * 4), "l"(coefA + idx), "r"(n)
-                     : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 3 * BW * 4), "l"(coefB + idx), "r"(n)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 3 * BW * 4), "l"(bb + off), "r"(n)
                      : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    const char* const src_o = reinterpret_cast<const char*>(o_src);
+    const char* const src_u = reinterpret_cast<const char*>(u_src);
+    const char* const src_a = reinterpret_cast<const char*>(coefA);
+    const char* const src_b = reinterpret_cast<const char*>(coefB);
 #pragma unroll
-    for (int j = 0; j < PF; ++j)
-        prefetch(r0 - T + j, j);   // rows of steps 0 .. PF-1
+    for (int j = 0; j < PF; ++j)   // rows of steps 0 .. PF-1
+        copy_row(src_o, src_u, src_a, src_b, boff + j * row_bytes, r0 - T + j, j);
+    // uniform bases shifted by the constant row distances
+    const char* const pf_o = src_o + PF * row_bytes;
+    const char* const pf_u = src_u + PF * row_bytes;
+    const char* const pf_a = src_a + PF * row_bytes;
+    const char* const pf_b = src_b + PF * row_bytes;
+    char* const st_o = reinterpret_cast<char*>(o_dst) - 2 * T * row_bytes;
+    char* const st_u = reinterpret_cast<char*>(u_dst) - 2 * T * row_bytes;
     __syncthreads();
 
     // One step of the pipeline.  ROWMASK selects the variant that applies the reference's top/bottom inclusion
@@ -137,9 +152,8 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                 if (pub_ok)
                     sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
             } else if (store_col && rho >= r0 && rho < r1) {
-                const size_t idx = static_cast<size_t>(rho) * L + colofs;
-                o_dst[idx] = on;
-                u_dst[idx] = un;
+                *reinterpret_cast<float*>(st_o + boff) = on;   // row rho = y_in - 2T
+                *reinterpret_cast<float*>(st_u + boff) = un;
             }
         }
         // level 0 arrives: the row of step s was requested PF steps ago.  Waiting is done every second step
@@ -156,7 +170,9 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             Ar[k % U] = st[2 * BW];
             Br[k % U] = st[3 * BW];
         }
-        prefetch(y_in + PF, k % PF);   // refill the slot just consumed (same thread: program order)
+        // refill the slot just consumed (same thread: program order) with the row PF steps ahead
+        copy_row(pf_o, pf_u, pf_a, pf_b, boff, y_in + PF, k % PF);
+        boff += row_bytes;
         // ONE barrier per TWO steps: a step reads ring slots (s-2)&3 (and its partner (s-1)&3) and writes
         // slot s&3 (partner (s+1)&3) -- disjoint, and what step s needs was published before the barrier
         // that closed step s-1 (worst-case visibility checked in tests/emul_stream_solver.py, sync_every=2)
