@@ -79,8 +79,9 @@ VSC_API uint64_t vsc_launch_count(void);
 VSC_API int vsc_correlation_f32(const float* in1, const float* in2, float* out, int N, int C, int H, int W,
     int max_displacement, int legacy, vsc_stream_t stream);
 
-/* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases), plain loads
- * otherwise;  1: always the plain-load stager.  Same arithmetic, same results.  For tests. */
+/* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases; 64x8 tiles
+ * for W >= 96, else 32x8), plain loads otherwise;  1: always the plain-load stager;  2 / 3: TMA with 32x8 / 64x8
+ * tiles.  Same arithmetic, bit-identical results.  For tests. */
 VSC_API int vsc_set_correlation_mode(int mode);
 
 /* custom::Warp: masked bilinear backward warp (warp.cc:71-134 / warp_cuda.cu:29-84).

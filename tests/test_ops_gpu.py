@@ -174,7 +174,7 @@ def test_ops_reject_bad_arguments(V, dev):
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 8, 32), (2, 12, 16, 20), (1, 196, 36, 60), (1, 64, 72, 120), (1, 5, 9, 44),
-                                   (1, 32, 136, 240)])
+                                   (1, 32, 136, 240), (2, 20, 23, 100), (1, 196, 34, 60)])
 @pytest.mark.parametrize("legacy", [False, True])
 def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, legacy):
     """W % 4 == 0: the TMA-staged kernel (default) and the plain-load stager run the same contraction."""
@@ -184,11 +184,17 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
     try:
         assert L.vsc_set_correlation_mode(1) == 0
         plain = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(2) == 0   # TMA, 32x8 tiles, 2 CTAs per SM
+        tma32 = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(3) == 0   # TMA, 64x8 tiles, software-pipelined, 1 CTA per SM
+        tma64 = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(0) == 0
-        tma = V.correlation(a, b, legacy=legacy)
-        tma2 = V.correlation(a, b, legacy=legacy)  # twice on the same stream (reference test.py:70-71)
+        auto = V.correlation(a, b, legacy=legacy)
+        auto2 = V.correlation(a, b, legacy=legacy)  # twice on the same stream (reference test.py:70-71)
     finally:
         L.vsc_set_correlation_mode(0)
     torch.cuda.synchronize()
-    assert torch.equal(tma, plain)
-    assert torch.equal(tma, tma2)
+    assert torch.equal(tma32, plain)
+    assert torch.equal(tma64, plain)
+    assert torch.equal(auto, plain)
+    assert torch.equal(auto, auto2)

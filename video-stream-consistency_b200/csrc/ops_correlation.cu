@@ -211,6 +211,122 @@ __global__ void __maxnreg__(128) correlation_md4_tma_kernel(
     correlation_store(out, acc, n, g, h0 + r, w0 + qc, H, W, divisor, legacy, vec_store);
 }
 
+// ---- wide TMA kernel: 64x8 tile, ONE CTA of 12 warps per SM, all of them consumers -------------------
+// The 32x8 kernel above is register-starved: two CTAs x (6 consumer + 1 producer warps) leave 128 registers
+// per thread, 108 of them accumulators, so every 128-bit LDS is consumed immediately and its latency is exposed
+// (ncu: short_scoreboard the top stall, FMA pipe 35 % busy).  Here a single CTA of exactly 12 warps owns the SM
+// (168 registers per thread): the in2 loads are software-pipelined one 128-bit load ahead of the FMAs, and the
+// TMA producer is simply lane 0 of warp 0, which refills the stage freed two iterations ago before computing.
+constexpr int kWTW = 64;                               // tile width
+constexpr int kWBW = kWTW + 2 * kMD;                   // 72 floats = 288 B rows
+constexpr int kWASize = kTH * kWTW;                    // 512
+constexpr int kWBSize = kBH * kWBW;                    // 1152
+constexpr int kWThreads = 384;                         // 128 pixel quads x 3 displacement groups
+constexpr int kWStageFloats = kKC * (kWASize + kWBSize);  // 13312 floats = 52 KB
+constexpr unsigned kWStageBytes = kWStageFloats * sizeof(float);
+
+__global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
+    const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out, int C,
+    int H, int W, float divisor, int legacy, int vec_store)
+{
+    extern __shared__ __align__(128) unsigned char smem_bytes[];
+    float* stage_mem = reinterpret_cast<float*>(smem_bytes);
+    __shared__ __align__(8) unsigned long long bars[2 * kStages];  // full[0..2], empty[0..2]
+
+    const int tid = threadIdx.x;
+    const int w0 = blockIdx.x * kWTW;
+    const int h0 = blockIdx.y * kTH;
+    const int n = blockIdx.z;
+    const int nchunks = (C + kKC - 1) / kKC;
+    const unsigned bar0 = smem_u32(bars);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar0 + 8 * i, 1);
+            mbar_init(bar0 + 8 * (kStages + i), kWThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int j) {  // thread 0 only: TMA for channel chunk j into stage j % kStages
+        const int s = j % kStages;
+        const unsigned full = bar0 + 8 * s;
+        mbar_expect_tx(full, kWStageBytes);
+        const unsigned dstA = smem_u32(stage_mem + s * kWStageFloats);
+        const unsigned dstB = dstA + kKC * kWASize * sizeof(float);
+        tma_load_4d(dstA, &mapA, full, w0, h0, j * kKC, n);
+        tma_load_4d(dstB, &mapB, full, w0 - kMD, h0 - kMD, j * kKC, n);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (nchunks > 1)
+            issue(1);
+    }
+
+    const int q = tid & 127;        // pixel quad inside the tile
+    const int g = tid >> 7;         // vertical displacement group (4 warps each)
+    const int r = q >> 4;           // tile row 0..7
+    const int qc = (q & 15) * 4;    // first tile column of the quad
+    float acc[3][kP][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < kP; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                acc[i][j][k] = 0.0f;
+
+    for (int j = 0; j < nchunks; ++j) {
+        const int s = j % kStages;
+        if (tid == 0 && j + 2 < nchunks) {  // refill the stage consumed at iteration j-1
+            if (j >= 1)
+                mbar_wait(bar0 + 8 * (kStages + (j + 2) % kStages), ((j + 2) / kStages - 1) & 1);
+            issue(j + 2);
+        }
+        mbar_wait(bar0 + 8 * s, (j / kStages) & 1);
+        const float* sA = stage_mem + s * kWStageFloats + r * kWTW + qc;
+        const float* sB = stage_mem + s * kWStageFloats + kKC * kWASize + (r + 3 * g) * kWBW + qc;
+        // software pipeline: the next 128-bit in2 load is in flight while the current one feeds 16 FMAs
+        float4 bn = *reinterpret_cast<const float4*>(sB);
+        float4 an = *reinterpret_cast<const float4*>(sA);
+#pragma unroll 1
+        for (int c = 0; c < kKC; ++c) {
+            const float av[4] = {an.x, an.y, an.z, an.w};
+            if (c + 1 < kKC)
+                an = *reinterpret_cast<const float4*>(sA + (c + 1) * kWASize);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    const float bv[4] = {bn.x, bn.y, bn.z, bn.w};
+                    // address of the load after (c, i, h)
+                    const int hn = (h + 1) % 3;
+                    const int in_ = (h == 2) ? (i + 1) % 3 : i;
+                    const bool wrap = (h == 2 && i == 2);
+                    if (!wrap || c + 1 < kKC)
+                        bn = *reinterpret_cast<const float4*>(sB + (c + (wrap ? 1 : 0)) * kWBSize + in_ * kWBW + 4 * hn);
+#pragma unroll
+                    for (int mm = 0; mm < 4; ++mm) {
+                        const int m = 4 * h + mm;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int jj = m - k;
+                            if (jj >= 0 && jj < kP)
+                                acc[i][jj][k] = __fmaf_rn(av[k], bv[mm], acc[i][jj][k]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0)
+            mbar_arrive(bar0 + 8 * (kStages + s));
+    }
+    correlation_store(out, acc, n, g, h0 + r, w0 + qc, H, W, divisor, legacy, vec_store);
+}
+
 // ---- plain-load stager for shapes TMA cannot address (W % 4 != 0 or unaligned bases) ----------------
 __global__ void __launch_bounds__(kConsumers) correlation_md4_ld_kernel(const float* __restrict__ in1,
     const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float divisor, int legacy,
@@ -335,13 +451,13 @@ static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int
         == CUDA_SUCCESS;
 }
 
-int g_corr_mode = 0;  // 0 auto, 1 force the plain-load stager (tests)
+int g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles (tests)
 
 }  // namespace vsc
 
 extern "C" int vsc_set_correlation_mode(int mode)
 {
-    if (mode < 0 || mode > 1)
+    if (mode < 0 || mode > 3)
         return VSC_E_INVALID;
     vsc::g_corr_mode = mode;
     return VSC_OK;
@@ -364,7 +480,28 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
         if (grid.y > 65535)
             return VSC_E_INVALID;
         const float divisor = static_cast<float>(C);
-        const bool tma_ok = g_corr_mode == 0 && (W % 4 == 0) && aligned16(in1) && aligned16(in2);
+        const bool tma_ok = g_corr_mode != 1 && (W % 4 == 0) && aligned16(in1) && aligned16(in2);
+        // wide tile when it is not mostly padding: image at least 1.5 tiles wide (mode 2 / 3 force 32 / 64)
+        const bool wide = g_corr_mode == 3 || (g_corr_mode == 0 && W >= 96);
+        if (tma_ok && wide) {
+            CUtensorMap mapA, mapB;
+            if (make_map(&mapA, in1, N, C, H, W, kWTW, kTH) && make_map(&mapB, in2, N, C, H, W, kWBW, kBH)) {
+                constexpr size_t smem = kStages * kWStageBytes;
+                static bool configured = false;
+                if (!configured) {
+                    const cudaError_t e = cudaFuncSetAttribute(correlation_md4_tma64_kernel,
+                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                    if (e != cudaSuccess)
+                        return static_cast<int>(e);
+                    configured = true;
+                }
+                const dim3 gridw(cdiv(W, kWTW), cdiv(H, kTH), N);
+                correlation_md4_tma64_kernel<<<gridw, kWThreads, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
+                    legacy ? 1 : 0, vec);
+                count_launch();
+                return launch_status();
+            }
+        }
         if (tma_ok) {
             CUtensorMap mapA, mapB;
             if (make_map(&mapA, in1, N, C, H, W, kTW, kTH) && make_map(&mapB, in2, N, C, H, W, kBW, kBH)) {
