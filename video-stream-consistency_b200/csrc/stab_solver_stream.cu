@@ -32,10 +32,13 @@
 
 namespace vsc {
 
-constexpr int kStreamPrefetch = 8;  // must divide the unroll factor 2T (T in {4, 8})
+constexpr int kStreamPrefetch = 8;  // private staging depth; must divide the unroll factor 2T (T in {4, 8})
+bool g_stream_coop = true;          // cooperative 16-byte staging when the images allow it (tests can turn it off)
 
 // BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best)
-template <int T, int BW>
+// COOP: level-0 rows staged cooperatively with 16-byte cp.async (one chunk per thread and row; needs 3W % 4 == 0
+// and 16-byte aligned images); otherwise every thread stages its own four floats with 4-byte cp.async.
+template <int T, int BW, bool COOP>
 __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
@@ -43,7 +46,8 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     constexpr int S = BW - 6 * T;   // columns stored per band
     constexpr int U = 2 * T;        // unroll: lcm(4, 2T) for T in {4, 8}
     static_assert(U % 4 == 0, "ring period");
-    constexpr int PF = kStreamPrefetch;  // rows in flight from HBM
+    constexpr int PF = COOP ? U : kStreamPrefetch;  // staging ring depth (rows in flight from HBM)
+    static_assert(BW % 64 == 0 && U % PF == 0, "staging geometry");
     extern __shared__ float smem_raw[];
     float* sm = smem_raw + 4;  // 4 floats of padding on each side: tid-3 / tid+3 never leave the allocation
     // thread-private staging ring for the level-0 rows: stage[slot][array][tid], filled by cp.async PF steps
@@ -90,6 +94,14 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     const unsigned stage_base = static_cast<unsigned>(__cvta_generic_to_shared(stage + tid));
     const long long row_bytes = static_cast<long long>(L) * 4;
     long long boff = (static_cast<long long>(r0 - T) * L + static_cast<long long>(colofs)) * 4;
+    const char* const src_o = reinterpret_cast<const char*>(o_src);
+    const char* const src_u = reinterpret_cast<const char*>(u_src);
+    const char* const src_a = reinterpret_cast<const char*>(coefA);
+    const char* const src_b = reinterpret_cast<const char*>(coefB);
+    char* const st_o = reinterpret_cast<char*>(o_dst) - 2 * T * row_bytes;
+    char* const st_u = reinterpret_cast<char*>(u_dst) - 2 * T * row_bytes;
+
+    // ---- private staging (COOP == false): 4 x 4-byte cp.async per thread and row, no cross-thread ordering
     auto copy_row = [&](const char* bo, const char* bu, const char* ba, const char* bb, long long off, int y,
                         int slot) {
         const unsigned n = (col_ok && y >= 0 && y < H) ? 4u : 0u;
@@ -102,20 +114,42 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                      : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const char* const src_o = reinterpret_cast<const char*>(o_src);
-    const char* const src_u = reinterpret_cast<const char*>(u_src);
-    const char* const src_a = reinterpret_cast<const char*>(coefA);
-    const char* const src_b = reinterpret_cast<const char*>(coefB);
-#pragma unroll
-    for (int j = 0; j < PF; ++j)   // rows of steps 0 .. PF-1
-        copy_row(src_o, src_u, src_a, src_b, boff + j * row_bytes, r0 - T + j, j);
-    // uniform bases shifted by the constant row distances
     const char* const pf_o = src_o + PF * row_bytes;
     const char* const pf_u = src_u + PF * row_bytes;
     const char* const pf_a = src_a + PF * row_bytes;
     const char* const pf_b = src_b + PF * row_bytes;
-    char* const st_o = reinterpret_cast<char*>(o_dst) - 2 * T * row_bytes;
-    char* const st_u = reinterpret_cast<char*>(u_dst) - 2 * T * row_bytes;
+
+    // ---- cooperative staging (COOP == true): a row of the four images is 4*BW floats = BW chunks of 16 bytes,
+    // exactly one chunk per thread: ONE 16-byte cp.async per thread and step instead of four 4-byte ones.
+    // Thread `tid` copies columns [g0 + 4*cg, +4) of image `arr`; chunks lie entirely inside or outside the
+    // image (3W % 4 == 0, g0 % 4 == 0).  The data is read by OTHER threads, so its arrival is ordered by the
+    // step barrier: a row is requested PF-2 steps early into the slot whose readers passed a barrier already,
+    // and every thread drains all but its PF-4 youngest groups before each barrier.
+    constexpr int kChunksPerArr = BW / 4;
+    const int arr = tid / kChunksPerArr;
+    const int cg = tid - arr * kChunksPerArr;
+    const int gcol = g0 + 4 * cg;
+    const bool chunk_ok = gcol >= 0 && gcol < L;
+    const char* const my_src = (arr == 0 ? src_o : arr == 1 ? src_u : arr == 2 ? src_a : src_b) + (PF - 2) * row_bytes;
+    long long my_off = (static_cast<long long>(r0 - T) * L + (chunk_ok ? gcol : 0)) * 4;   // row of step s
+    const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + 4 * cg));
+    auto coop_copy = [&](const char* src, int y, int slot) {
+        const unsigned n = (chunk_ok && y >= 0 && y < H) ? 16u : 0u;
+        const unsigned d = my_dst + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if constexpr (COOP) {
+#pragma unroll
+        for (int j = 0; j < PF - 2; ++j)   // rows of steps 0 .. PF-3
+            coop_copy(my_src - (PF - 2) * row_bytes + my_off + j * row_bytes, r0 - T + j, j);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+#pragma unroll
+        for (int j = 0; j < PF; ++j)       // rows of steps 0 .. PF-1
+            copy_row(src_o, src_u, src_a, src_b, boff + j * row_bytes, r0 - T + j, j);
+    }
     __syncthreads();
 
     // One step of the pipeline.  ROWMASK selects the variant that applies the reference's top/bottom inclusion
@@ -158,8 +192,10 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         }
         // level 0 arrives: the row of step s was requested PF steps ago.  Waiting is done every second step
         // for two rows at once: at an even step at most PF-2 younger groups may still be in flight
-        if ((k & 1) == 0)
-            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");
+        if constexpr (!COOP) {
+            if ((k & 1) == 0)
+                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");
+        }
         {
             const float* st = stage + (k % PF) * 4 * BW + tid;
             const float n_o = st[0];
@@ -170,8 +206,16 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             Ar[k % U] = st[2 * BW];
             Br[k % U] = st[3 * BW];
         }
-        // refill the slot just consumed (same thread: program order) with the row PF steps ahead
-        copy_row(pf_o, pf_u, pf_a, pf_b, boff, y_in + PF, k % PF);
+        if constexpr (COOP) {
+            // request the row of step s+PF-2 into the slot read at step s-2 (its readers passed a barrier)
+            coop_copy(my_src + my_off, y_in + PF - 2, (k + PF - 2) % PF);
+            my_off += row_bytes;
+            if ((k & 1) == 1)
+                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 4) : "memory");
+        } else {
+            // refill the slot just consumed (same thread: program order) with the row PF steps ahead
+            copy_row(pf_o, pf_u, pf_a, pf_b, boff, y_in + PF, k % PF);
+        }
         boff += row_bytes;
         // ONE barrier per TWO steps: a step reads ring slots (s-2)&3 (and its partner (s-1)&3) and writes
         // slot s&3 (partner (s+1)&3) -- disjoint, and what step s needs was published before the barrier
@@ -220,24 +264,36 @@ static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
     return g;
 }
 
-template <int T, int BW>
-static int launch_stream(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
+template <int T, int BW, bool COOP>
+static int launch_stream_impl(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
-    const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + kStreamPrefetch * 4 * BW) * sizeof(float);
+    constexpr int PF = COOP ? 2 * T : kStreamPrefetch;
+    const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T, BW>,
+        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T, BW, COOP>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess)
             return static_cast<int>(e);
         configured = true;
     }
     const dim3 grid(g.nb, g.nc);
-    solver_stream_kernel<T, BW><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
+    solver_stream_kernel<T, BW, COOP><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
         step, mom);
     count_launch();
     return launch_status();
+}
+
+template <int T, int BW>
+static int launch_stream(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
+    float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+{
+    const bool coop = (3LL * W) % 4 == 0 && aligned16(coefA) && aligned16(coefB) && aligned16(u_src) && aligned16(o_src)
+        && g_stream_coop;
+    if (coop)
+        return launch_stream_impl<T, BW, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    return launch_stream_impl<T, BW, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
 }
 
 template <int T>
