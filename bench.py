@@ -212,6 +212,7 @@ def bench_ours(args, rank, world):
     d_flf, d_flb = torch.from_numpy(flf).to(dev), torch.from_numpy(flb).to(dev)
     sets = make_op_tensors(wl, dev)
     hpar = V.HyperParams()
+    V.check(V.lib().vsc_set_solver_mode(args.solver_mode))
 
     # ---------------- device-resident arm: every input already in HBM ----------------
     d_o = [V.image_to_gpu(x.to(dev)) for x in ho]
@@ -325,7 +326,7 @@ def bench_ours(args, rank, world):
     L.vsc_set_solver_mode(1)
     time_solve(8)
     sweep_ms = (time_solve(2 * n) - time_solve(n)) / n
-    L.vsc_set_solver_mode(0)
+    L.vsc_set_solver_mode(args.solver_mode)
     alg_bytes = 8 * 72.0 * W * H
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
     unblocked = 72.0 * W * H / (sweep_ms * 1e-3) / 1e9
@@ -481,6 +482,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-light", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver-mode", type=lambda x: int(x, 0), default=0, help="vsc_set_solver_mode value (A/B runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -120,6 +120,8 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  *   0  auto (default): temporally blocked passes (8 / 4 sweeps per launch, intermediate sweeps kept on chip)
  *      for images of at least 128x48, single unblocked sweeps otherwise and for the numIter % 4 remainder;
  *   1  unblocked sweeps only;   2  blocked passes whenever numIter >= 4, whatever the image size.
+ * Two flag bits select variants of the blocked kernel (same results): | 0x10 = CTA-wide barrier instead of
+ * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging.
  * Process-wide; meant for tests and benchmarks. */
 VSC_API int vsc_set_solver_mode(int mode);
 

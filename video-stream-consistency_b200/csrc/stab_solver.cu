@@ -170,6 +170,7 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st);
 
 int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
+extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
 
 // how `iters` sweeps are executed: n8 passes of 8 sweeps, n4 passes of 4, `rest` single unblocked sweeps
 struct SweepPlan {
@@ -264,9 +265,11 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 
 extern "C" int vsc_set_solver_mode(int mode)
 {
-    if (mode < 0 || mode > 2)
+    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x3F)
         return VSC_E_INVALID;
-    g_solver_mode = mode;
+    g_solver_mode = mode & 0xF;
+    g_stream_pair = (mode & 0x10) == 0;
+    g_stream_coop = (mode & 0x20) == 0;
     return VSC_OK;
 }
 

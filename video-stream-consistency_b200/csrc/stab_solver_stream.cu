@@ -33,12 +33,14 @@
 namespace vsc {
 
 constexpr int kStreamPrefetch = 8;  // private staging depth; must divide the unroll factor 2T (T in {4, 8})
-bool g_stream_coop = true;          // cooperative 16-byte staging when the images allow it (tests can turn it off)
+bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
+bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
 
 // BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best)
-// COOP: level-0 rows staged cooperatively with 16-byte cp.async (one chunk per thread and row; needs 3W % 4 == 0
-// and 16-byte aligned images); otherwise every thread stages its own four floats with 4-byte cp.async.
-template <int T, int BW, bool COOP>
+// COOP: level-0 rows staged warp-cooperatively with 16-byte cp.async (one chunk per lane and row; needs
+// 3W % 4 == 0 and 16-byte aligned images); otherwise every thread stages its own four floats (4-byte cp.async).
+// PAIR: the exchange ring is synchronised between neighbouring warps only (named barriers).
+template <int T, int BW, bool COOP, bool PAIR>
 __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
@@ -119,20 +121,20 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     const char* const pf_a = src_a + PF * row_bytes;
     const char* const pf_b = src_b + PF * row_bytes;
 
-    // ---- cooperative staging (COOP == true): a row of the four images is 4*BW floats = BW chunks of 16 bytes,
-    // exactly one chunk per thread: ONE 16-byte cp.async per thread and step instead of four 4-byte ones.
-    // Thread `tid` copies columns [g0 + 4*cg, +4) of image `arr`; chunks lie entirely inside or outside the
-    // image (3W % 4 == 0, g0 % 4 == 0).  The data is read by OTHER threads, so its arrival is ordered by the
-    // step barrier: a row is requested PF-2 steps early into the slot whose readers passed a barrier already,
-    // and every thread drains all but its PF-4 youngest groups before each barrier.
-    constexpr int kChunksPerArr = BW / 4;
-    const int arr = tid / kChunksPerArr;
-    const int cg = tid - arr * kChunksPerArr;
-    const int gcol = g0 + 4 * cg;
+    // ---- warp-cooperative staging (COOP == true): the 32 columns of a warp x 4 images are 32 chunks of 16 bytes,
+    // exactly one per lane: ONE 16-byte cp.async per thread and step instead of four 4-byte ones.  Lane l copies
+    // columns [g0 + 32*warp + 4*(l%8), +4) of image l/8; chunks lie entirely inside or outside the image
+    // (3W % 4 == 0, g0 % 4 == 0).  Producer and consumers of a chunk are lanes of the SAME warp, so the only
+    // ordering needed is cp.async.wait_group + __syncwarp: a row is requested PF-1 steps early, into the slot
+    // the warp read one step earlier.
+    const int lane = tid & 31;
+    const int arr = lane >> 3;
+    const int wcol = (tid & ~31) + 4 * (lane & 7);   // first column (inside the band) of my chunk
+    const int gcol = g0 + wcol;
     const bool chunk_ok = gcol >= 0 && gcol < L;
-    const char* const my_src = (arr == 0 ? src_o : arr == 1 ? src_u : arr == 2 ? src_a : src_b) + (PF - 2) * row_bytes;
+    const char* const my_src = (arr == 0 ? src_o : arr == 1 ? src_u : arr == 2 ? src_a : src_b) + (PF - 1) * row_bytes;
     long long my_off = (static_cast<long long>(r0 - T) * L + (chunk_ok ? gcol : 0)) * 4;   // row of step s
-    const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + 4 * cg));
+    const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + wcol));
     auto coop_copy = [&](const char* src, int y, int slot) {
         const unsigned n = (chunk_ok && y >= 0 && y < H) ? 16u : 0u;
         const unsigned d = my_dst + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
@@ -142,15 +144,35 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
 
     if constexpr (COOP) {
 #pragma unroll
-        for (int j = 0; j < PF - 2; ++j)   // rows of steps 0 .. PF-3
-            coop_copy(my_src - (PF - 2) * row_bytes + my_off + j * row_bytes, r0 - T + j, j);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int j = 0; j < PF - 1; ++j)   // rows of steps 0 .. PF-2
+            coop_copy(my_src - (PF - 1) * row_bytes + my_off + j * row_bytes, r0 - T + j, j);
     } else {
 #pragma unroll
         for (int j = 0; j < PF; ++j)       // rows of steps 0 .. PF-1
             copy_row(src_o, src_u, src_a, src_b, boff + j * row_bytes, r0 - T + j, j);
     }
     __syncthreads();
+
+    // Synchronisation of the neighbour-exchange ring.  A thread only ever reads columns tid+-3, i.e. its own
+    // warp or an adjacent one, so instead of a CTA-wide barrier each warp synchronises with its two neighbours
+    // through named barriers (id i = the boundary between warps i-1 and i, 64 threads each).  Even warps take
+    // left then right, odd warps right then left, so all boundaries complete in two rounds instead of rippling.
+    // Warps that are not neighbours may drift apart, which spreads the LDS-heavy and FMA-heavy phases of the
+    // step over time instead of having all warps hit the same pipe at once.
+    constexpr int NW = BW / 32;
+    const int warp = tid >> 5;
+    auto ring_sync = [&]() {
+        if constexpr (PAIR && NW <= 16) {
+            const int first = (warp & 1) ? warp + 1 : warp;   // boundary ids: left = warp, right = warp + 1
+            const int second = (warp & 1) ? warp : warp + 1;
+            if (first >= 1 && first <= NW - 1)
+                asm volatile("bar.sync %0, 64;" ::"r"(first) : "memory");
+            if (second >= 1 && second <= NW - 1)
+                asm volatile("bar.sync %0, 64;" ::"r"(second) : "memory");
+        } else {
+            __syncthreads();
+        }
+    };
 
     // One step of the pipeline.  ROWMASK selects the variant that applies the reference's top/bottom inclusion
     // tests (flowconsistency.cu:227,232); it is needed only while some level works on rows <= 0 or >= H-2, a
@@ -192,7 +214,13 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         }
         // level 0 arrives: the row of step s was requested PF steps ago.  Waiting is done every second step
         // for two rows at once: at an even step at most PF-2 younger groups may still be in flight
-        if constexpr (!COOP) {
+        if constexpr (COOP) {
+            // the row of step s was requested at step s-PF+1: all but the PF-2 youngest groups must be done;
+            // __syncwarp makes the other lanes' chunks visible and closes the previous step's reads of the slot
+            // that is refilled below
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");
+            __syncwarp();
+        } else {
             if ((k & 1) == 0)
                 asm volatile("cp.async.wait_group %0;" ::"n"(PF - 2) : "memory");
         }
@@ -207,11 +235,9 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             Br[k % U] = st[3 * BW];
         }
         if constexpr (COOP) {
-            // request the row of step s+PF-2 into the slot read at step s-2 (its readers passed a barrier)
-            coop_copy(my_src + my_off, y_in + PF - 2, (k + PF - 2) % PF);
+            // request the row of step s+PF-1 into the slot this warp read at step s-1
+            coop_copy(my_src + my_off, y_in + PF - 1, (k + PF - 1) % PF);
             my_off += row_bytes;
-            if ((k & 1) == 1)
-                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 4) : "memory");
         } else {
             // refill the slot just consumed (same thread: program order) with the row PF steps ahead
             copy_row(pf_o, pf_u, pf_a, pf_b, boff, y_in + PF, k % PF);
@@ -221,7 +247,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         // slot s&3 (partner (s+1)&3) -- disjoint, and what step s needs was published before the barrier
         // that closed step s-1 (worst-case visibility checked in tests/emul_stream_solver.py, sync_every=2)
         if ((k & 1) == 1)
-            __syncthreads();
+            ring_sync();
     };
 
     for (int base = 0; base < nsteps; base += U) {
@@ -264,7 +290,7 @@ static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
     return g;
 }
 
-template <int T, int BW, bool COOP>
+template <int T, int BW, bool COOP, bool PAIR>
 static int launch_stream_impl(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
@@ -272,14 +298,14 @@ static int launch_stream_impl(const StreamGeom& g, const float* coefA, const flo
     const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T, BW, COOP>,
+        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T, BW, COOP, PAIR>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess)
             return static_cast<int>(e);
         configured = true;
     }
     const dim3 grid(g.nb, g.nc);
-    solver_stream_kernel<T, BW, COOP><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
+    solver_stream_kernel<T, BW, COOP, PAIR><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
         step, mom);
     count_launch();
     return launch_status();
@@ -291,9 +317,12 @@ static int launch_stream(const StreamGeom& g, const float* coefA, const float* c
 {
     const bool coop = (3LL * W) % 4 == 0 && aligned16(coefA) && aligned16(coefB) && aligned16(u_src) && aligned16(o_src)
         && g_stream_coop;
+    if (coop && g_stream_pair)
+        return launch_stream_impl<T, BW, true, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (coop)
-        return launch_stream_impl<T, BW, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-    return launch_stream_impl<T, BW, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        return launch_stream_impl<T, BW, true, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom,
+            st);
+    return launch_stream_impl<T, BW, false, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
 }
 
 template <int T>
