@@ -172,10 +172,11 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
 
-// how `iters` sweeps are executed: n8 passes of 8 sweeps, n4 passes of 4, `rest` single unblocked sweeps
+// how `iters` sweeps are executed: n8 passes of 8 sweeps, one pass of `tail` in {0,2,4,6} sweeps, `rest` in {0,1}
+// single unblocked sweeps (150 = 18x8 + 6, 75 = 9x8 + 2 + 1)
 struct SweepPlan {
-    int n8, n4, rest;
-    int flips() const { return n8 + n4 + rest; }  // number of out-buffer ping-pongs
+    int n8, tail, rest;
+    int flips() const { return n8 + (tail ? 1 : 0) + rest; }  // number of out-buffer ping-pongs
 };
 
 static SweepPlan plan_sweeps(int W, int H, int iters)
@@ -184,10 +185,10 @@ static SweepPlan plan_sweeps(int W, int H, int iters)
     // tiny images: the 3T-step pipeline fill and the 6T-float band halo dominate -> plain sweeps
     const bool big = H >= 48 && 3 * W >= 384;
     if (g_solver_mode == 1 || (g_solver_mode == 0 && !big))
-        return p;
+        return p;  // {0, 0, iters}
     p.n8 = iters / 8;
-    p.n4 = (iters % 8) / 4;
-    p.rest = iters % 4;
+    p.tail = (iters % 8) & ~1;
+    p.rest = iters & 1;
     return p;
 }
 
@@ -202,8 +203,9 @@ static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, i
     float* us = b.u;
     float* ud = b.u2;
     int rc = VSC_OK;
-    for (int k = 0; k < plan.n8 + plan.n4 && rc == VSC_OK; ++k) {
-        rc = solver_stream_pass(k < plan.n8 ? 8 : 4, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
+    const int npass = plan.n8 + (plan.tail ? 1 : 0);
+    for (int k = 0; k < npass && rc == VSC_OK; ++k) {
+        rc = solver_stream_pass(k < plan.n8 ? 8 : plan.tail, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
         float* t = src; src = dst; dst = t;
         t = us; us = ud; ud = t;
     }

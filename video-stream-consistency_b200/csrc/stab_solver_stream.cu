@@ -32,7 +32,8 @@
 
 namespace vsc {
 
-constexpr int kStreamPrefetch = 8;  // private staging depth; must divide the unroll factor 2T (T in {4, 8})
+// private staging depth: divides the unroll factor 2T (T in {2, 4, 6, 8})
+__host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 : (T == 2 ? 4 : 8); }
 bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
 bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
 
@@ -48,8 +49,8 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     constexpr int S = BW - 6 * T;   // columns stored per band
     constexpr int U = 2 * T;        // unroll: lcm(4, 2T) for T in {4, 8}
     static_assert(U % 4 == 0, "ring period");
-    constexpr int PF = COOP ? U : kStreamPrefetch;  // staging ring depth (rows in flight from HBM)
-    static_assert(BW % 64 == 0 && U % PF == 0, "staging geometry");
+    constexpr int PF = COOP ? U : stream_private_pf(T);  // staging ring depth (rows in flight from HBM)
+    static_assert(BW % 64 == 0 && U % PF == 0 && PF >= 4, "staging geometry: slot index = step mod PF = k mod PF");
     extern __shared__ float smem_raw[];
     float* sm = smem_raw + 4;  // 4 floats of padding on each side: tid-3 / tid+3 never leave the allocation
     // thread-private staging ring for the level-0 rows: stage[slot][array][tid], filled by cp.async PF steps
@@ -294,7 +295,7 @@ template <int T, int BW, bool COOP, bool PAIR>
 static int launch_stream_impl(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
-    constexpr int PF = COOP ? 2 * T : kStreamPrefetch;
+    constexpr int PF = COOP ? 2 * T : stream_private_pf(T);
     const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static bool configured = false;
     if (!configured) {
@@ -354,8 +355,12 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 {
     if (T == 8)
         return launch_stream_best<8>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    if (T == 6)
+        return launch_stream_best<6>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (T == 4)
         return launch_stream_best<4>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    if (T == 2)
+        return launch_stream_best<2>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     return VSC_E_INVALID;
 }
 
