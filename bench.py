@@ -219,7 +219,7 @@ def bench_ours(args, rank, world):
     d_p = [V.image_to_gpu(x.to(dev)) for x in hp]
     last = d_p[2].clone()
     cons = torch.empty_like(last)
-    ws = torch.empty(int(V.lib().vsc_frame_solve_workspace_bytes(W, H, hpar.pyramidLevels)), device=dev,
+    ws = torch.empty(int(V.lib().vsc_frame_stabilize_workspace_bytes(W, H, hpar.pyramidLevels)), device=dev,
                      dtype=torch.uint8)
     lowres = (fw, fh) != (W, H)
     upf = torch.empty((H, W, 3), device=dev) if lowres else d_flf
@@ -243,9 +243,8 @@ def bench_ours(args, rank, world):
             V.check(L.vsc_bilinear(dptr(d_flf), fw, fh, 3, dptr(upf), W, H, 3, stream()))
             V.check(L.vsc_bilinear(dptr(d_flb), fw, fh, 3, dptr(upb), W, H, 3, stream()))
         i0, i1, i2 = stream_frame_index(t)
-        _, aP, wt = V.stage_a_fused(d_o[i0], d_o[i1], d_o[i2], d_p[i0], d_p[i1], d_p[i2], last, upf, upb,
-                                    hpar.alpha, hpar.beta, hpar.gamma)
-        V.frame_solve(d_p[i1], aP, wt, hpar, workspace=ws, out=cons)
+        V.frame_stabilize(d_o[i0], d_o[i1], d_o[i2], d_p[i0], d_p[i1], d_p[i2], last, upf, upb, hpar, out=cons,
+                          workspace=ws)
         V.check(L.vsc_f32x3_to_rgba8(dptr(cons), dptr(out8), W, H, stream()))
         last, cons = cons, last
 
@@ -396,6 +395,7 @@ def cpu_frame(O, wl, band_h, state):
 def cpu_state(O, wl, band_h):
     import synth
 
+    O.use_all_cores()
     W, H = wl["W"], band_h
     o8, p8 = synth.frames(W, H, 3, seed=1234)
     ffl, fbl = synth.flows(W, H, 3)

@@ -121,7 +121,8 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  *      for images of at least 128x48, single unblocked sweeps otherwise and for the numIter % 4 remainder;
  *   1  unblocked sweeps only;   2  blocked passes whenever numIter >= 4, whatever the image size.
  * Two flag bits select variants of the blocked kernel (same results): | 0x10 = CTA-wide barrier instead of
- * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging.
+ * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging;
+ * | 0x40 = vsc_frame_stabilize never takes its fused path.
  * Process-wide; meant for tests and benchmarks. */
 VSC_API int vsc_set_solver_mode(int mode);
 
@@ -159,6 +160,18 @@ VSC_API size_t vsc_frame_solve_workspace_bytes(int W, int H, int pyramidLevels);
 VSC_API int vsc_frame_solve(const float* procCur, const float* adapCmbPr, const float* consWt,
     const vsc_hyper_params* p, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
     vsc_stream_t stream);
+
+/* Stage A + pyramid + solve in one call: everything doOneStep does between retrieveOpticalFlow and
+ * copyToQImage (videostabilizer.cpp:182-228) on device images.  With two pyramid levels and even W, H the
+ * adaptive combination, the consistency weight, the level-0 solver coefficients and the level-1 inputs come
+ * out of ONE kernel (no adapCmbPr / consWt round trip through HBM, no separate down-scales); otherwise it is
+ * vsc_stage_a_fused + vsc_frame_solve.  Results are bit-identical either way.
+ * workspace >= vsc_frame_stabilize_workspace_bytes(W,H,levels). */
+VSC_API size_t vsc_frame_stabilize_workspace_bytes(int W, int H, int pyramidLevels);
+VSC_API int vsc_frame_stabilize(const float* origPrev, const float* origCur, const float* origNext,
+    const float* procPrev, const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd,
+    const float* flowBwd, int flow_channels, const vsc_hyper_params* p, float* consisOut, int W, int H,
+    void* workspace, size_t workspace_bytes, vsc_stream_t stream);
 
 /* ------------------------------------------------------------------ per-stream pipeline object
  * Mirror of VideoStabilizer's recurrence (videostabilizer.cpp:136-153,167-265) for ONE video

@@ -64,6 +64,16 @@ def num_threads() -> int:
     return int(lib().vsc_oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Size the OpenMP team to the cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().vsc_oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 # ---------------------------------------------------------------- custom ops (NCHW fp32)
 def correlation(in1, in2, max_displacement: int = 4, legacy: bool = False) -> np.ndarray:
     """custom::Correlation.  legacy=False -> [N,P,P,H,W]; legacy=True -> [N,P*P,H,W] divided by C."""

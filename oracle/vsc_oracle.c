@@ -463,6 +463,17 @@ int vsc_oracle_do_one_step(const float* origPrev, const float* origCur, const fl
     return rc;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets the team size explicitly */
+void vsc_oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int vsc_oracle_num_threads(void)
 {
     int n = 1;

@@ -377,3 +377,27 @@ def test_blocked_solver_full_frame_pipeline(V, O, dev):
     assert ok, msg
     assert np.abs(out.astype(np.int32) - ref[0][1].astype(np.int32)).max() <= 1
     st.close()
+
+
+@pytest.mark.parametrize("W,H,levels", [(64, 48, 2), (320, 192, 2), (46, 38, 2), (45, 37, 2), (64, 48, 1), (64, 48, 3)])
+@pytest.mark.parametrize("fc", [3, 2])
+def test_frame_stabilize_fused_equals_unfused(V, dev, W, H, levels, fc):
+    """vsc_frame_stabilize: the fused stage-A + solver set-up path (2 levels, even sizes) must reproduce
+    vsc_stage_a_fused + vsc_frame_solve bit for bit; other shapes take the generic path."""
+    o8, p8 = synth.frames(W, H, 3, seed=93, mismatch=0.2)
+    of = [V.image_to_gpu(cu(x, dev)) for x in o8]
+    pf = [V.image_to_gpu(cu(x, dev)) for x in p8]
+    ff, fb = (cu(x, dev) for x in synth.flows(W, H, fc))
+    hp = V.HyperParams(pyramidLevels=levels, numIter=40)
+    _, aP, wt = V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[2], ff, fb, hp.alpha, hp.beta, hp.gamma)
+    ref = V.frame_solve(pf[1], aP, wt, hp)
+    L = V.lib()
+    try:
+        got = V.frame_stabilize(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[2], ff, fb, hp)
+        assert L.vsc_set_solver_mode(0x40) == 0
+        got_generic = V.frame_stabilize(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[2], ff, fb, hp)
+    finally:
+        L.vsc_set_solver_mode(0)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert torch.equal(got_generic, ref)

@@ -51,6 +51,72 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const float* __restrict__ 
     consWt[v] = consist_wt_value(ci, ai, beta, gamma);
 }
 
+// Stage A fused with the solver set-up of the fine pyramid level (and the coarse level's inputs):
+// instead of writing adapCmbPr / consWt (24 B/px), re-reading them with the processed frame in
+// solver_prepare_kernel (36 B/px read, 36 B/px written) and three times more in the pyramid-down resizes,
+// each thread folds its value straight into the level-0 solver coefficients
+//     A = -step*(cnt + w)      B = step*(w*tgt - lap(pr))          (same expressions as solver_prepare_kernel)
+// and, for pixels with even x and y, also stores (pr, tgt, w) into the half-resolution level-1 inputs: with even
+// W and H the reference's get_bilinear down-scale (flowconsistency.cu:50-75, no half-pixel offset) samples
+// exactly those pixels with weights (1,0,0,0).  Results are bit-identical to the unfused sequence.
+__global__ void __launch_bounds__(256) stage_a_prep_kernel(const float* __restrict__ origPrev,
+    const float* __restrict__ origCur, const float* __restrict__ origNext, const float* __restrict__ procPrev,
+    const float* __restrict__ procCur, const float* __restrict__ procNext, const float* __restrict__ lastStab,
+    const float* __restrict__ flowFwd, const float* __restrict__ flowBwd, int flowC, float alpha, float beta,
+    float gamma, float step, float* __restrict__ coefA, float* __restrict__ coefB, float* __restrict__ pr1,
+    float* __restrict__ tg1, float* __restrict__ wt1, int W, int H)
+{
+    const int L = 3 * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float index inside the row
+    const int iy = blockIdx.y;
+    if (i >= L)
+        return;
+    const int ix = i / 3;
+    const int c = i - 3 * ix;
+    const size_t p = static_cast<size_t>(iy) * W + ix;
+    const size_t v = p * 3 + c;
+    const WarpGeom gb = hwc_warp_geom(ix, iy, __ldg(flowBwd + p * flowC), __ldg(flowBwd + p * flowC + 1), W, H);
+    const WarpGeom gf = hwc_warp_geom(ix, iy, __ldg(flowFwd + p * flowC), __ldg(flowFwd + p * flowC + 1), W, H);
+    const float pi = hwc_warp_sample1(origPrev, W, gb, c);
+    const float pp = hwc_warp_sample1(procPrev, W, gb, c);
+    const float ni = hwc_warp_sample1(origNext, W, gf, c);
+    const float np = hwc_warp_sample1(procNext, W, gf, c);
+    const float ls = hwc_warp_sample1(lastStab, W, gb, c);
+    const float ci = ldg_stream(origCur + v);
+    const float cp = __ldg(procCur + v);
+    float ai, tgt;
+    adap_comb_value(ci, cp, pi, pp, ni, np, ls, alpha, ai, tgt);
+    const float w = consist_wt_value(ci, ai, beta, gamma);
+    // Laplacian of the processed frame with the reference's inclusion tests (flowconsistency.cu:215-238)
+    int cnt = 0;
+    float lap = 0.0f;
+    if ((ix + 1) < (W - 1)) { lap += __ldg(procCur + v + 3); cnt += 1; }
+    if ((ix - 1) >= 0)      { lap += __ldg(procCur + v - 3); cnt += 1; }
+    if ((iy + 1) < (H - 1)) { lap += __ldg(procCur + v + L); cnt += 1; }
+    if ((iy - 1) >= 0)      { lap += __ldg(procCur + v - L); cnt += 1; }
+    lap -= static_cast<float>(cnt) * cp;
+    coefA[v] = -step * (static_cast<float>(cnt) + w);
+    coefB[v] = step * (w * tgt - lap);
+    if (((ix | iy) & 1) == 0) {
+        const size_t v1 = (static_cast<size_t>(iy >> 1) * (W >> 1) + (ix >> 1)) * 3 + c;
+        pr1[v1] = cp;
+        tg1[v1] = tgt;
+        wt1[v1] = w;
+    }
+}
+
+int launch_stage_a_prep(const float* origPrev, const float* origCur, const float* origNext, const float* procPrev,
+    const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd, const float* flowBwd,
+    int flowC, float alpha, float beta, float gamma, float step, float* coefA, float* coefB, float* pr1, float* tg1,
+    float* wt1, int W, int H, cudaStream_t st)
+{
+    const dim3 grid(cdiv(3LL * W, 256), H);
+    stage_a_prep_kernel<<<grid, 256, 0, st>>>(origPrev, origCur, origNext, procPrev, procCur, procNext, lastStab,
+        flowFwd, flowBwd, flowC, alpha, beta, gamma, step, coefA, coefB, pr1, tg1, wt1, W, H);
+    count_launch();
+    return launch_status();
+}
+
 }  // namespace vsc
 
 extern "C" int vsc_stage_a_fused(const float* origPrev, const float* origCur, const float* origNext,

@@ -171,6 +171,7 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 
 int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
+bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
 // how `iters` sweeps are executed: n8 passes of 8 sweeps, one pass of `tail` in {0,2,4,6} sweeps, `rest` in {0,1}
 // single unblocked sweeps (150 = 18x8 + 6, 75 = 9x8 + 2 + 1)
@@ -267,11 +268,12 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 
 extern "C" int vsc_set_solver_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x3F)
+    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x7F)
         return VSC_E_INVALID;
     g_solver_mode = mode & 0xF;
     g_stream_pair = (mode & 0x10) == 0;
     g_stream_coop = (mode & 0x20) == 0;
+    g_frame_fused = (mode & 0x40) == 0;
     return VSC_OK;
 }
 
@@ -320,17 +322,25 @@ extern "C" size_t vsc_frame_solve_workspace_bytes(int W, int H, int pyramidLevel
     return total;
 }
 
-extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, const float* consWt,
-    const vsc_hyper_params* p, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
-    vsc_stream_t stream)
+namespace vsc {
+int launch_stage_a_prep(const float* origPrev, const float* origCur, const float* origNext, const float* procPrev,
+    const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd, const float* flowBwd,
+    int flowC, float alpha, float beta, float gamma, float step, float* coefA, float* coefB, float* pr1, float* tg1,
+    float* wt1, int W, int H, cudaStream_t st);
+}
+
+// stageA != nullptr: the fused path -- level-0 coefficients and the level-1 inputs are produced by
+// stage_a_prep_kernel (2 levels, even W and H) instead of by solver_prepare_kernel + three resizes
+struct StageAInputs {
+    const float *origPrev, *origCur, *origNext, *procPrev, *procNext, *lastStab, *flowFwd, *flowBwd;
+    int flowC;
+};
+
+static int frame_solve_impl(const float* procCur, const float* adapCmbPr, const float* consWt,
+    const vsc_hyper_params* p, float* consisOut, int W, int H, void* workspace, vsc_stream_t stream,
+    const StageAInputs* stageA)
 {
-    if (!procCur || !adapCmbPr || !consWt || !p || !consisOut || W <= 0 || H <= 0 || H > 65535)
-        return VSC_E_INVALID;
     const int levels = p->pyramidLevels;
-    if (levels < 1 || levels > kMaxLevels || p->numIter < 0)
-        return VSC_E_INVALID;
-    if (!workspace || workspace_bytes < vsc_frame_solve_workspace_bytes(W, H, levels) || !aligned16(workspace))
-        return VSC_E_WORKSPACE;
     const LevelDims d = level_dims(W, H, levels);
     if (d.w[levels - 1] < 1 || d.h[levels - 1] < 1)
         return VSC_E_INVALID;
@@ -361,9 +371,18 @@ extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, con
     }
 
     int rc;
+    if (stageA) {
+        rc = launch_stage_a_prep(stageA->origPrev, stageA->origCur, stageA->origNext, stageA->procPrev, procCur,
+            stageA->procNext, stageA->lastStab, stageA->flowFwd, stageA->flowBwd, stageA->flowC, p->alpha, p->beta,
+            p->gamma, p->stepSize, sb[0].coefA, sb[0].coefB, const_cast<float*>(pr[1]), const_cast<float*>(tg[1]),
+            const_cast<float*>(wt[1]), W, H, st);
+        if (rc) return rc;
+        const cudaError_t e = cudaMemsetAsync(sb[0].u, 0, d.n[0] * sizeof(float), st);  // momentum starts at 0
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
     // pyramid down (videostabilizer.cpp:210-216).  pyrConsisOut[0] is a copy of the processed frame (:209),
     // so its downsampled version equals pyrPr[j] -- computed once and copied.
-    for (int j = 1; j < levels; ++j) {
+    for (int j = 1; j < levels && !stageA; ++j) {
         rc = vsc_bilinear(pr[j - 1], d.w[j - 1], d.h[j - 1], 3, const_cast<float*>(pr[j]), d.w[j], d.h[j], 3, stream);
         if (rc) return rc;
         rc = vsc_bilinear(tg[j - 1], d.w[j - 1], d.h[j - 1], 3, const_cast<float*>(tg[j]), d.w[j], d.h[j], 3, stream);
@@ -391,12 +410,67 @@ extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, con
             rc = vsc_bilinear(coarse_result, d.w[j + 1], d.h[j + 1], 3, x, d.w[j], d.h[j], 3, stream);
             if (rc) return rc;
         }
-        rc = launch_prepare(pr[j], tg[j], wt[j], sb[j], copy_src, copy_dst, d.w[j], d.h[j], p->stepSize, st);
-        if (rc) return rc;
+        if (!(stageA && j == 0)) {
+            rc = launch_prepare(pr[j], tg[j], wt[j], sb[j], copy_src, copy_dst, d.w[j], d.h[j], p->stepSize, st);
+            if (rc) return rc;
+        }
         float* res = nullptr;
         rc = run_sweeps(sb[j], x, y, d.w[j], d.h[j], iters, p->stepSize, p->momFac, st, &res);
         if (rc) return rc;
         coarse_result = res;  // == final_buf (also when iters == 0: x == final_buf since 0 is even)
     }
     return VSC_OK;
+}
+
+extern "C" int vsc_frame_solve(const float* procCur, const float* adapCmbPr, const float* consWt,
+    const vsc_hyper_params* p, float* consisOut, int W, int H, void* workspace, size_t workspace_bytes,
+    vsc_stream_t stream)
+{
+    if (!procCur || !adapCmbPr || !consWt || !p || !consisOut || W <= 0 || H <= 0 || H > 65535)
+        return VSC_E_INVALID;
+    const int levels = p->pyramidLevels;
+    if (levels < 1 || levels > kMaxLevels || p->numIter < 0)
+        return VSC_E_INVALID;
+    if (!workspace || workspace_bytes < vsc_frame_solve_workspace_bytes(W, H, levels) || !aligned16(workspace))
+        return VSC_E_WORKSPACE;
+    return frame_solve_impl(procCur, adapCmbPr, consWt, p, consisOut, W, H, workspace, stream, nullptr);
+}
+
+extern "C" size_t vsc_frame_stabilize_workspace_bytes(int W, int H, int pyramidLevels)
+{
+    const size_t base = vsc_frame_solve_workspace_bytes(W, H, pyramidLevels);
+    if (base == 0)
+        return 0;
+    return base + 2 * align_up(static_cast<size_t>(W) * H * 3 * sizeof(float));  // adapCmbPr, consWt (generic path)
+}
+
+extern "C" int vsc_frame_stabilize(const float* origPrev, const float* origCur, const float* origNext,
+    const float* procPrev, const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd,
+    const float* flowBwd, int flow_channels, const vsc_hyper_params* p, float* consisOut, int W, int H,
+    void* workspace, size_t workspace_bytes, vsc_stream_t stream)
+{
+    if (!origPrev || !origCur || !origNext || !procPrev || !procCur || !procNext || !lastStab || !flowFwd || !flowBwd
+        || !p || !consisOut || W < 2 || H < 2 || H > 65535 || (flow_channels != 2 && flow_channels != 3))
+        return VSC_E_INVALID;
+    const int levels = p->pyramidLevels;
+    if (levels < 1 || levels > kMaxLevels || p->numIter < 0)
+        return VSC_E_INVALID;
+    if (!workspace || workspace_bytes < vsc_frame_stabilize_workspace_bytes(W, H, levels) || !aligned16(workspace))
+        return VSC_E_WORKSPACE;
+    if (level_dims(W, H, levels).w[levels - 1] < 1 || level_dims(W, H, levels).h[levels - 1] < 1)
+        return VSC_E_INVALID;
+    const bool fused = levels == 2 && (W % 2 == 0) && (H % 2 == 0) && g_frame_fused;
+    if (fused) {
+        const StageAInputs in{origPrev, origCur, origNext, procPrev, procNext, lastStab, flowFwd, flowBwd,
+            flow_channels};
+        return frame_solve_impl(procCur, nullptr, nullptr, p, consisOut, W, H, workspace, stream, &in);
+    }
+    char* extra = static_cast<char*>(workspace) + vsc_frame_solve_workspace_bytes(W, H, levels);
+    float* tgt = reinterpret_cast<float*>(extra);
+    float* wt = reinterpret_cast<float*>(extra + align_up(static_cast<size_t>(W) * H * 3 * sizeof(float)));
+    const int rc = vsc_stage_a_fused(origPrev, origCur, origNext, procPrev, procCur, procNext, lastStab, flowFwd,
+        flowBwd, flow_channels, p->alpha, p->beta, p->gamma, nullptr, tgt, wt, W, H, stream);
+    if (rc)
+        return rc;
+    return frame_solve_impl(procCur, tgt, wt, p, consisOut, W, H, workspace, stream, nullptr);
 }

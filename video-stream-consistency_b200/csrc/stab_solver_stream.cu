@@ -34,6 +34,7 @@ namespace vsc {
 
 // private staging depth: divides the unroll factor 2T (T in {2, 4, 6, 8})
 __host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 : (T == 2 ? 4 : 8); }
+__host__ __device__ constexpr int stream_halo(int T) { return (3 * T + 3) / 4 * 4; }
 bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
 bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
 
@@ -46,7 +47,9 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
 {
-    constexpr int S = BW - 6 * T;   // columns stored per band
+    // band halo: 3 floats per sweep, rounded up to a multiple of 4 so that band starts stay 16-byte aligned
+    constexpr int HALO = stream_halo(T);
+    constexpr int S = BW - 2 * HALO;   // columns stored per band
     constexpr int U = 2 * T;        // unroll: lcm(4, 2T) for T in {4, 8}
     static_assert(U % 4 == 0, "ring period");
     constexpr int PF = COOP ? U : stream_private_pf(T);  // staging ring depth (rows in flight from HBM)
@@ -59,12 +62,12 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
 
     const int tid = threadIdx.x;
     const int L = 3 * W;
-    const int g0 = blockIdx.x * S - 3 * T;
+    const int g0 = blockIdx.x * S - HALO;
     const int gi = g0 + tid;
     const int r0 = blockIdx.y * chunk_rows;
     const int r1 = min(H, r0 + chunk_rows);
     const bool col_ok = gi >= 0 && gi < L;
-    const bool store_col = col_ok && tid >= 3 * T && tid < 3 * T + S;
+    const bool store_col = col_ok && tid >= HALO && tid < HALO + S;
     // publishes to the neighbour-exchange ring: image columns except the last pixel column (see step_body)
     const bool pub_ok = col_ok && gi < 3 * (W - 1);
     const int nsteps = (r1 - r0) + 3 * T;
@@ -277,7 +280,7 @@ struct StreamGeom {
 static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
 {
     StreamGeom g;
-    const int S = BW - 6 * T;
+    const int S = BW - 2 * stream_halo(T);
     g.nb = (L + S - 1) / S;
     int nc = sms / g.nb;
     if (nc < 1) nc = 1;

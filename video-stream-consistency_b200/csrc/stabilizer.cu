@@ -51,7 +51,7 @@ struct vsc_stabilizer {
     int head = 0, count = 0;
     long long pushed = 0;
 
-    float *lastStab = nullptr, *consisOut = nullptr, *adapCmbPr = nullptr, *consWt = nullptr;
+    float *lastStab = nullptr, *consisOut = nullptr;
     float* flowUp[2] = {};
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -96,7 +96,7 @@ int ensure_workspace(vsc_stabilizer* s, int levels)
 {
     if (levels == s->ws_levels)
         return VSC_OK;
-    const size_t need = vsc_frame_solve_workspace_bytes(s->W, s->H, levels);
+    const size_t need = vsc_frame_stabilize_workspace_bytes(s->W, s->H, levels);
     if (need == 0)
         return VSC_E_INVALID;
     if (need > s->ws_bytes) {
@@ -129,13 +129,8 @@ int do_step(vsc_stabilizer* s, const float* flowFwd, const float* flowBwd, uint8
         if ((rc = cu(cudaStreamWaitEvent(s->compute, s->slot_ready[k], 0))))
             return rc;
 
-    rc = vsc_stage_a_fused(s->orig[s0], s->orig[s1], s->orig[s2], s->proc[s0], s->proc[s1], s->proc[s2], s->lastStab,
-        flowFwd, flowBwd, s->flowC, c.alpha, c.beta, c.gamma, nullptr, s->adapCmbPr, s->consWt, s->W, s->H,
-        s->compute);
-    if (rc)
-        return rc;
-    rc = vsc_frame_solve(s->proc[s1], s->adapCmbPr, s->consWt, &c, s->consisOut, s->W, s->H, s->ws, s->ws_bytes,
-        s->compute);
+    rc = vsc_frame_stabilize(s->orig[s0], s->orig[s1], s->orig[s2], s->proc[s0], s->proc[s1], s->proc[s2],
+        s->lastStab, flowFwd, flowBwd, s->flowC, &c, s->consisOut, s->W, s->H, s->ws, s->ws_bytes, s->compute);
     if (rc)
         return rc;
 
@@ -221,8 +216,6 @@ extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flo
     }
     dmalloc(reinterpret_cast<void**>(&s->lastStab), fb);
     dmalloc(reinterpret_cast<void**>(&s->consisOut), fb);
-    dmalloc(reinterpret_cast<void**>(&s->adapCmbPr), fb);
-    dmalloc(reinterpret_cast<void**>(&s->consWt), fb);
     for (int i = 0; i < 2; ++i) {
         dmalloc(reinterpret_cast<void**>(&s->flowUp[i]), s->P * flow_channels * sizeof(float));
         dmalloc(reinterpret_cast<void**>(&s->out_dev[i]), s->P * 4);
@@ -260,8 +253,6 @@ extern "C" void vsc_stabilizer_destroy(vsc_stabilizer* s)
     }
     cudaFree(s->lastStab);
     cudaFree(s->consisOut);
-    cudaFree(s->adapCmbPr);
-    cudaFree(s->consWt);
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->flowUp[i]);
         cudaFree(s->out_dev[i]);

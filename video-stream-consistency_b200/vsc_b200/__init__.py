@@ -25,7 +25,7 @@ from ._lib import LIB_PATH, VscError, check, lib
 __all__ = [
     "LIB_PATH", "VscError", "lib", "launch_count", "correlation", "warp", "get_warp_result", "get_adap_comb",
     "get_consist_wt", "get_bilinear", "get_consist_out", "image_to_gpu", "gpu_to_image", "stage_a_fused",
-    "frame_solve", "HyperParams", "Stabilizer", "pinned_empty",
+    "frame_solve", "frame_stabilize", "HyperParams", "Stabilizer", "pinned_empty",
 ]
 
 
@@ -202,6 +202,24 @@ def frame_solve(procCur, adapCmbPr, consWt, params: HyperParams, workspace: torc
     check(lib().vsc_frame_solve(_f32(procCur, "procCur"), _f32(adapCmbPr, "adapCmbPr"), _f32(consWt, "consWt"),
                                 C.byref(params), _f32(out, "consisOut"), W, H, C.c_void_p(workspace.data_ptr()),
                                 C.c_size_t(workspace.numel()), _stream()))
+    return out
+
+
+def frame_stabilize(origPrev, origCur, origNext, procPrev, procCur, procNext, lastStab, flowFwd, flowBwd,
+                    params: HyperParams, out: torch.Tensor | None = None,
+                    workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """Stage A + pyramid + solve of one frame (doOneStep between the flow and the 8-bit conversion)."""
+    H, W = _hw3(origCur, "origCur")
+    nbytes = int(lib().vsc_frame_stabilize_workspace_bytes(W, H, params.pyramidLevels))
+    ws = workspace if workspace is not None else torch.empty(nbytes, device=origCur.device, dtype=torch.uint8)
+    nbytes = ws.numel()
+    if out is None:
+        out = torch.empty_like(origCur)
+    check(lib().vsc_frame_stabilize(_f32(origPrev, "origPrev"), _f32(origCur, "origCur"), _f32(origNext, "origNext"),
+                                    _f32(procPrev, "procPrev"), _f32(procCur, "procCur"), _f32(procNext, "procNext"),
+                                    _f32(lastStab, "lastStab"), _f32(flowFwd, "flowFwd"), _f32(flowBwd, "flowBwd"),
+                                    int(flowFwd.shape[2]), C.byref(params), _f32(out, "consisOut"), W, H,
+                                    C.c_void_p(ws.data_ptr()), C.c_size_t(nbytes), _stream()))
     return out
 
 

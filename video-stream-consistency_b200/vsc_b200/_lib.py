@@ -38,6 +38,8 @@ PROTOTYPES = {
     "vsc_hyper_params_default": (None, [_p]),
     "vsc_frame_solve_workspace_bytes": (_sz, [_i, _i, _i]),
     "vsc_frame_solve": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
+    "vsc_frame_stabilize_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vsc_frame_stabilize": (_i, [_p] * 9 + [_i, _p, _p, _i, _i, _p, _sz, _p]),
     "vsc_stabilizer_create": (_i, [_p, _i, _i, _i]),
     "vsc_stabilizer_destroy": (None, [_p]),
     "vsc_stabilizer_hyper_params": (_p, [_p]),
