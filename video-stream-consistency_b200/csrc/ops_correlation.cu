@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(256) correlation_generic_kernel(const float* _
     if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) {
         const float* a = in1 + static_cast<size_t>(n) * C * HW + static_cast<size_t>(h) * W + w;
         const float* b = in2 + static_cast<size_t>(n) * C * HW + static_cast<size_t>(h2) * W + w2;
+#pragma unroll 8
         for (int c = 0; c < C; ++c)
             acc = __fmaf_rn(__ldg(a + c * HW), __ldg(b + c * HW), acc);
     }
@@ -474,7 +475,12 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
     if (!aligned4(in1) || !aligned4(in2) || !aligned4(out))
         return VSC_E_ALIGN;
     cudaStream_t st = as_stream(stream);
-    if (max_displacement == kMD) {
+    // Small maps (the coarse PWC-Net levels: 9x15 ... 36x60 at 1080p/2) give the tiled kernels a handful of CTAs
+    // that each walk all channels serially (76 us for 196x9x15, two CTAs).  One thread per output value spreads
+    // the same work over 81*H*W threads, with both operands L1/L2-resident: a few microseconds.  Same FMA chain
+    // per value, so the results are bit-identical to the tiled kernels.
+    const bool small_map = max_displacement == kMD && g_corr_mode == 0 && static_cast<long long>(H) * W <= 4096;
+    if (max_displacement == kMD && !small_map) {
         const int vec = (W % 4 == 0) && aligned16(out);
         const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), N);
         if (grid.y > 65535)
