@@ -203,6 +203,12 @@ VSC_API int vsc_stabilizer_step(vsc_stabilizer* s, const float* flowFwd_dev, con
  * vsc_bilinear semantics (values not rescaled, as the reference) inside the step */
 VSC_API int vsc_stabilizer_step_lowres_flow(vsc_stabilizer* s, const float* flowFwd_dev, const float* flowBwd_dev,
     int flowW, int flowH, uint8_t* out_rgba_host);
+/* same, flows given in HOST memory (precomputed-flow mode, BASELINE config 4: what FileStabilizer reads from
+ * frame_%06d.flo / frame_%06d_bwd.flo with ReadFlowFile, stabilizefiles.cpp:134-149): HWC float, flow_channels
+ * per pixel (2 for .flo), at flowW x flowH; uploaded on the copy stream (pinned buffers directly, pageable ones
+ * through pinned staging), up-sampled like _step_lowres_flow if smaller than the frame. */
+VSC_API int vsc_stabilizer_step_host_flow(vsc_stabilizer* s, const float* flowFwd_host, const float* flowBwd_host,
+    int flowW, int flowH, uint8_t* out_rgba_host);
 VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
 /* device pointer to the fp32 result of the last step (W*H*3 floats), for tests */
 VSC_API const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s);

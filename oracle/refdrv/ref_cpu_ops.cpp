@@ -12,6 +12,8 @@
 #include <ort_custom_ops/opticalflow/warp.h>
 #include <ort_custom_ops/custom_ops.h>
 
+#include "flowIO.h"  // the reference's Middlebury .flo reader/writer (src/stabilization/flowIO.cpp), unmodified
+
 #include <cstdio>
 #include <cstring>
 #include <exception>
@@ -121,6 +123,34 @@ int vsc_ref_cpu_registry(char* buf, size_t n)
         }
     std::snprintf(buf, n, "%s", s.c_str());
     return count;
+}
+
+// ReadFlowFile / WriteFlowFile of the reference (flowIO.cpp:31-107) on caller buffers; 0 ok, 1 = it threw
+int vsc_ref_read_flo(const char* path, float* buf, size_t cap_floats, int* w, int* h)
+{
+    try {
+        std::vector<float> flow;
+        ReadFlowFile(flow, *w, *h, path);
+        if (flow.size() > cap_floats)
+            return 2;
+        std::memcpy(buf, flow.data(), flow.size() * sizeof(float));
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_ref_read_flo: %s\n", e.what());
+        return 1;
+    }
+}
+
+int vsc_ref_write_flo(const char* path, const float* buf, int w, int h)
+{
+    try {
+        std::vector<float> flow(buf, buf + static_cast<size_t>(w) * h * 2);
+        WriteFlowFile(flow, w, h, path);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_ref_write_flo: %s\n", e.what());
+        return 1;
+    }
 }
 
 // missing-attribute behaviour of the reference ctor (correlation.h:19-31): returns 1 if it threw

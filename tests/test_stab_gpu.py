@@ -401,3 +401,54 @@ def test_frame_stabilize_fused_equals_unfused(V, dev, W, H, levels, fc):
     torch.cuda.synchronize()
     assert torch.equal(got, ref)
     assert torch.equal(got_generic, ref)
+
+
+def _write_flo(path, flow2):
+    """Middlebury .flo (flowIO.cpp:5-22): 'PIEH', int32 width, int32 height, interleaved float32 u,v rows."""
+    h, w, _ = flow2.shape
+    with open(path, "wb") as f:
+        f.write(b"PIEH")
+        f.write(np.array([w, h], np.int32).tobytes())
+        f.write(np.ascontiguousarray(flow2, np.float32).tobytes())
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (50, 30)])
+def test_precomputed_flow_files_mode(V, O, dev, tmp_path, W, H):
+    """BASELINE config 4 (-f <flowdir>): 2-channel flows read from frame_%06d.flo / frame_%06d_bwd.flo (with the
+    reference's own ReadFlowFile when oracle/_ref is present) and handed to the pipeline from HOST memory."""
+    o8, p8 = synth.frames(W, H, 4, seed=95)
+    ff, fb = synth.flows(W, H, 2)
+    fwd_path, bwd_path = str(tmp_path / "frame_000002.flo"), str(tmp_path / "frame_000001_bwd.flo")
+    _write_flo(fwd_path, ff)
+    _write_flo(bwd_path, fb)
+    if O.ref_cpu_available():
+        import ctypes as C
+        L = O.ref_cpu()
+        buf = np.zeros((H, W, 2), np.float32)
+        w, h = C.c_int(0), C.c_int(0)
+        assert L.vsc_ref_read_flo(fwd_path.encode(), buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), C.byref(w),
+                                  C.byref(h)) == 0
+        assert (w.value, h.value) == (W, H) and np.array_equal(buf, ff)
+        rff = buf.copy()
+        assert L.vsc_ref_read_flo(bwd_path.encode(), buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), C.byref(w),
+                                  C.byref(h)) == 0
+        rfb = buf.copy()
+        assert L.vsc_ref_read_flo(str(tmp_path / "missing.flo").encode(), buf.ctypes.data_as(C.c_void_p),
+                                  C.c_size_t(buf.size), C.byref(w), C.byref(h)) == 1   # throws like the reference
+    else:
+        rff, rfb = ff, fb
+    ref = _oracle_sequence(O, o8, p8, rff, rfb, (1, 2), dict(numIter=30))
+    st = V.Stabilizer(W, H, 2)
+    st.hyper_params.numIter = 30
+    for t in range(3):
+        st.push_frame(o8[t], p8[t])
+    outs = [np.zeros((H, W, 4), np.uint8) for _ in range(2)]
+    st.step_host_flow(rff, rfb, outs[0])
+    st.push_frame(o8[3], p8[3])
+    st.step_host_flow(torch.from_numpy(rff).pin_memory(), torch.from_numpy(rfb).pin_memory(), outs[1])
+    st.sync()
+    for i in range(2):
+        assert np.abs(outs[i].astype(np.int32) - ref[i][1].astype(np.int32)).max() <= 1
+    with pytest.raises(V.VscError):
+        st.step_host_flow(ff, fb)   # window not refilled
+    st.close()

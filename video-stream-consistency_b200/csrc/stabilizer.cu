@@ -53,6 +53,10 @@ struct vsc_stabilizer {
 
     float *lastStab = nullptr, *consisOut = nullptr;
     float* flowUp[2] = {};
+    float* flowIn[2] = {};      // device landing buffers for host flows (frame-sized)
+    float* flowPin[2] = {};     // pinned staging for pageable host flows
+    cudaEvent_t flow_ready = nullptr, flow_free = nullptr;
+    bool flow_used = false;
     void* ws = nullptr;
     size_t ws_bytes = 0;
     int ws_levels = 0;
@@ -218,11 +222,15 @@ extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flo
     dmalloc(reinterpret_cast<void**>(&s->consisOut), fb);
     for (int i = 0; i < 2; ++i) {
         dmalloc(reinterpret_cast<void**>(&s->flowUp[i]), s->P * flow_channels * sizeof(float));
+        dmalloc(reinterpret_cast<void**>(&s->flowIn[i]), s->P * flow_channels * sizeof(float));
+        hmalloc(reinterpret_cast<void**>(&s->flowPin[i]), s->P * flow_channels * sizeof(float));
         dmalloc(reinterpret_cast<void**>(&s->out_dev[i]), s->P * 4);
         hmalloc(reinterpret_cast<void**>(&s->out_pin[i]), s->P * 4);
         mkevent(&s->out_conv[i]);
         mkevent(&s->out_done[i]);
     }
+    mkevent(&s->flow_ready);
+    mkevent(&s->flow_free);
     if (!rc)
         rc = ensure_workspace(s, s->hp.pyramidLevels);
     if (rc) {
@@ -255,11 +263,15 @@ extern "C" void vsc_stabilizer_destroy(vsc_stabilizer* s)
     cudaFree(s->consisOut);
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->flowUp[i]);
+        cudaFree(s->flowIn[i]);
+        cudaFreeHost(s->flowPin[i]);
         cudaFree(s->out_dev[i]);
         cudaFreeHost(s->out_pin[i]);
         if (s->out_conv[i]) cudaEventDestroy(s->out_conv[i]);
         if (s->out_done[i]) cudaEventDestroy(s->out_done[i]);
     }
+    if (s->flow_ready) cudaEventDestroy(s->flow_ready);
+    if (s->flow_free) cudaEventDestroy(s->flow_free);
     cudaFree(s->ws);
     if (s->compute) cudaStreamDestroy(s->compute);
     if (s->copy) cudaStreamDestroy(s->copy);
@@ -339,6 +351,47 @@ extern "C" int vsc_stabilizer_step_lowres_flow(vsc_stabilizer* s, const float* f
     if (rc)
         return rc;
     return do_step(s, s->flowUp[0], s->flowUp[1], out_rgba_host);
+}
+
+extern "C" int vsc_stabilizer_step_host_flow(vsc_stabilizer* s, const float* flowFwd_host, const float* flowBwd_host,
+    int flowW, int flowH, uint8_t* out_rgba_host)
+{
+    if (!s || !flowFwd_host || !flowBwd_host || flowW <= 0 || flowH <= 0 || flowW > s->W || flowH > s->H)
+        return VSC_E_INVALID;
+    if (s->count != 3)
+        return VSC_E_STATE;
+    const size_t bytes = static_cast<size_t>(flowW) * flowH * s->flowC * sizeof(float);
+    int rc;
+    // the landing buffers were read by the previous host-flow step on the compute stream
+    if (s->flow_used && (rc = cu(cudaStreamWaitEvent(s->copy, s->flow_free, 0))))
+        return rc;
+    const float* src[2] = {flowFwd_host, flowBwd_host};
+    for (int i = 0; i < 2; ++i) {
+        const float* from = src[i];
+        if (!is_pinned(from)) {
+            if (s->flow_used)
+                cudaEventSynchronize(s->flow_ready);  // previous H2D out of the pinned staging finished
+            std::memcpy(s->flowPin[i], from, bytes);
+            from = s->flowPin[i];
+        }
+        if ((rc = cu(cudaMemcpyAsync(s->flowIn[i], from, bytes, cudaMemcpyHostToDevice, s->copy))))
+            return rc;
+    }
+    cudaEventRecord(s->flow_ready, s->copy);
+    s->flow_used = true;
+    if ((rc = cu(cudaStreamWaitEvent(s->compute, s->flow_ready, 0))))
+        return rc;
+    if (flowW == s->W && flowH == s->H) {
+        rc = do_step(s, s->flowIn[0], s->flowIn[1], out_rgba_host);
+    } else {
+        rc = vsc_bilinear(s->flowIn[0], flowW, flowH, s->flowC, s->flowUp[0], s->W, s->H, s->flowC, s->compute);
+        if (!rc)
+            rc = vsc_bilinear(s->flowIn[1], flowW, flowH, s->flowC, s->flowUp[1], s->W, s->H, s->flowC, s->compute);
+        if (!rc)
+            rc = do_step(s, s->flowUp[0], s->flowUp[1], out_rgba_host);
+    }
+    cudaEventRecord(s->flow_free, s->compute);
+    return rc;
 }
 
 extern "C" int vsc_stabilizer_sync(vsc_stabilizer* s)

@@ -279,6 +279,27 @@ class Stabilizer:
             check(lib().vsc_stabilizer_step_lowres_flow(self._h, _f32(flowFwd, "flowFwd"), _f32(flowBwd, "flowBwd"),
                                                         fw, fh, outp))
 
+    def step_host_flow(self, flowFwd_host, flowBwd_host, out_rgba_host=None):
+        """doOneStep with precomputed flows in HOST memory (.flo mode): float32 [h,w,flow_channels] arrays."""
+        import numpy as np
+
+        def fptr(t, name):
+            if isinstance(t, torch.Tensor):
+                if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise VscError(f"{name}: expected a contiguous float32 HOST tensor")
+                return C.c_void_p(t.data_ptr()), int(t.shape[1]), int(t.shape[0]), int(t.shape[2])
+            if not (isinstance(t, np.ndarray) and t.dtype == np.float32 and t.flags["C_CONTIGUOUS"]):
+                raise VscError(f"{name}: expected a contiguous float32 host array")
+            return C.c_void_p(t.ctypes.data), int(t.shape[1]), int(t.shape[0]), int(t.shape[2])
+
+        pf, fw, fh, fc = fptr(flowFwd_host, "flowFwd")
+        pb, bw, bh, bc = fptr(flowBwd_host, "flowBwd")
+        if (fw, fh, fc) != (bw, bh, bc) or fc != self.flow_channels:
+            raise VscError("step_host_flow: flows must have the same shape and the stabilizer's channel count")
+        self._keep_flow = [flowFwd_host, flowBwd_host]
+        outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
+        check(lib().vsc_stabilizer_step_host_flow(self._h, pf, pb, fw, fh, outp))
+
     def sync(self):
         check(lib().vsc_stabilizer_sync(self._h))
 
