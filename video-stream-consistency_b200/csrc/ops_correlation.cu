@@ -493,14 +493,9 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
             CUtensorMap mapA, mapB;
             if (make_map(&mapA, in1, N, C, H, W, kWTW, kTH) && make_map(&mapB, in2, N, C, H, W, kWBW, kBH)) {
                 constexpr size_t smem = kStages * kWStageBytes;
-                static bool configured = false;
-                if (!configured) {
-                    const cudaError_t e = cudaFuncSetAttribute(correlation_md4_tma64_kernel,
-                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-                    if (e != cudaSuccess)
-                        return static_cast<int>(e);
-                    configured = true;
-                }
+                static unsigned long long configured = 0;
+                if (const int e = ensure_dynamic_smem(correlation_md4_tma64_kernel, smem, false, configured))
+                    return e;
                 const dim3 gridw(cdiv(W, kWTW), cdiv(H, kTH), N);
                 correlation_md4_tma64_kernel<<<gridw, kWThreads, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
                     legacy ? 1 : 0, vec);
@@ -512,17 +507,9 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
             CUtensorMap mapA, mapB;
             if (make_map(&mapA, in1, N, C, H, W, kTW, kTH) && make_map(&mapB, in2, N, C, H, W, kBW, kBH)) {
                 constexpr size_t smem = kStages * kStageBytes;
-                static bool configured = false;
-                if (!configured) {
-                    cudaError_t e = cudaFuncSetAttribute(correlation_md4_tma_kernel,
-                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-                    if (e == cudaSuccess)  // two 84 KB CTAs per SM need the large shared-memory carve-out
-                        e = cudaFuncSetAttribute(correlation_md4_tma_kernel,
-                            cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                    if (e != cudaSuccess)
-                        return static_cast<int>(e);
-                    configured = true;
-                }
+                static unsigned long long configured = 0;  // two 84 KB CTAs per SM need the max-shared carve-out
+                if (const int e = ensure_dynamic_smem(correlation_md4_tma_kernel, smem, true, configured))
+                    return e;
                 correlation_md4_tma_kernel<<<grid, kConsumers + 32, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
                     legacy ? 1 : 0, vec);
                 count_launch();

@@ -300,14 +300,9 @@ static int launch_stream_impl(const StreamGeom& g, const float* coefA, const flo
 {
     constexpr int PF = COOP ? 2 * T : stream_private_pf(T);
     const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(solver_stream_kernel<T, BW, COOP, PAIR>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess)
-            return static_cast<int>(e);
-        configured = true;
-    }
+    static unsigned long long configured = 0;
+    if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, COOP, PAIR>, smem, false, configured))
+        return e;
     const dim3 grid(g.nb, g.nc);
     solver_stream_kernel<T, BW, COOP, PAIR><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
         step, mom);

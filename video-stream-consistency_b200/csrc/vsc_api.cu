@@ -8,18 +8,22 @@ unsigned long long g_launches = 0;
 
 int sm_count()
 {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess
-            && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
+    static int cached[64] = {};
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 148;  // B200; not cached so that a later call with a device present re-queries
+    }
+    int& slot = cached[dev & 63];
+    if (slot == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            slot = n;
         else {
             (void)cudaGetLastError();
-            return 148;  // B200; not cached so that a later call with a device present re-queries
+            return 148;
         }
     }
-    return cached;
+    return slot;
 }
 
 }  // namespace vsc

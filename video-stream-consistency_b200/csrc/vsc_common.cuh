@@ -33,6 +33,26 @@ inline unsigned cdiv(long long a, long long b) { return static_cast<unsigned>((a
 // number of SMs of the current device (cached); B200 = 148
 int sm_count();
 
+// Opt a kernel into `smem` bytes of dynamic shared memory (and optionally the max-shared carve-out).  Function
+// attributes are per device, so the "already done" flag is a bit per device ordinal, not one per process.
+template <class Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t smem, bool max_carveout, unsigned long long& done_mask)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return static_cast<int>(cudaGetLastError());
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&done_mask, __ATOMIC_ACQUIRE) & bit)
+        return VSC_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess && max_carveout)
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess)
+        return static_cast<int>(e);
+    __atomic_fetch_or(&done_mask, bit, __ATOMIC_RELEASE);
+    return VSC_OK;
+}
+
 // streaming (read-once) loads/stores: do not allocate in L1
 __device__ __forceinline__ float4 ldg_stream4(const float* p)
 {
