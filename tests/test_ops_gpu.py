@@ -108,11 +108,20 @@ def test_correlation_full_size_properties(V, dev):
 
 
 # ---------------------------------------------------------------- Warp
+@pytest.fixture(params=[1, 2], ids=["linear", "tiled"])
+def warp_mode(V, request):
+    """every Warp test runs on both kernels (vsc_set_warp_mode)"""
+    assert V.lib().vsc_set_warp_mode(request.param) == 0
+    yield request.param
+    V.lib().vsc_set_warp_mode(0)
+
+
 @pytest.mark.parametrize("shape,sigma", [
     ((1, 1, 2, 2), 1.0), ((2, 5, 13, 21), 5.0), ((1, 8, 16, 12), 0.5), ((1, 64, 18, 30), 2.0), ((2, 3, 33, 64), 3.0),
-    ((1, 4, 7, 100), 40.0), ((1, 96, 36, 60), 2.0),
+    ((1, 4, 7, 100), 40.0), ((1, 96, 36, 60), 2.0), ((1, 3, 1, 1), 0.3), ((2, 2, 1, 9), 0.8), ((1, 2, 9, 1), 0.8),
+    ((1, 5, 2, 40), 1.5), ((3, 9, 40, 2), 1.5),
 ])
-def test_warp_vs_oracle(V, O, dev, shape, sigma):
+def test_warp_vs_oracle(V, O, dev, shape, sigma, warp_mode):
     N, C, H, W = shape
     x = synth.features(N, C, H, W, 7)
     f = synth.op_flow(N, H, W, 8, sigma)
@@ -123,7 +132,7 @@ def test_warp_vs_oracle(V, O, dev, shape, sigma):
     assert np.array_equal(got == 0, ref == 0)
 
 
-def test_warp_golden(V, dev):
+def test_warp_golden(V, dev, warp_mode):
     g = np.load(GOLD)
     for name in ("warp_big", "warp_testpy", "warp_edge"):
         got = V.warp(cu(g[name + "_in"], dev), cu(g[name + "_flow"], dev)).cpu().numpy()
@@ -132,7 +141,7 @@ def test_warp_golden(V, dev):
         assert np.array_equal(got == 0, ref == 0), name
 
 
-def test_warp_nonfinite(V, O, dev):
+def test_warp_nonfinite(V, O, dev, warp_mode):
     """NaN / inf flow and non-finite input values outside the sampled taps must behave like the reference."""
     x = synth.features(1, 2, 6, 8, 9)
     f = synth.op_flow(1, 6, 8, 10, 1.0)
@@ -145,7 +154,7 @@ def test_warp_nonfinite(V, O, dev):
     assert rel(np.nan_to_num(got), np.nan_to_num(ref)) <= TOL
 
 
-def test_warp_identity_and_shift(V, dev):
+def test_warp_identity_and_shift(V, dev, warp_mode):
     """size-independent properties at the dense-4K level-2 shape: zero flow is the identity; an integer shift
     is a translation with zeros where the source leaves the image."""
     C, H, W = 32, 544, 960
@@ -160,6 +169,25 @@ def test_warp_identity_and_shift(V, dev):
     ref = torch.zeros_like(x)
     ref[:, :, 2:H, 0:W - 3] = x[:, :, 0:H - 2, 3:W]
     assert torch.equal(out, ref)
+
+
+def test_warp_kernels_agree(V, dev):
+    """the tiled kernel (shared 2x2 gather quad, border corners re-slotted) equals the one-pixel-per-thread
+    kernel value for value, including every border case a large random flow produces"""
+    g = torch.Generator(device=dev).manual_seed(17)
+    for (N, C, H, W) in ((2, 12, 67, 131), (1, 7, 5, 3), (1, 4, 2, 2), (1, 33, 40, 64)):
+        x = torch.randn((N, C, H, W), device=dev, generator=g)
+        f = 6.0 * torch.randn((N, 2, H, W), device=dev, generator=g)
+        f[:, :, ::3, ::2] = torch.round(f[:, :, ::3, ::2])  # integer displacements: alpha/beta exactly 0 at borders
+        try:
+            assert V.lib().vsc_set_warp_mode(1) == 0
+            a = V.warp(x, f)
+            assert V.lib().vsc_set_warp_mode(2) == 0
+            b = V.warp(x, f)
+        finally:
+            V.lib().vsc_set_warp_mode(0)
+        assert torch.equal(a, b), (N, C, H, W)
+    assert V.lib().vsc_set_warp_mode(3) == -1
 
 
 def test_ops_reject_bad_arguments(V, dev):
@@ -188,6 +216,8 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
         tma32 = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(3) == 0   # TMA, 64x8 tiles, software-pipelined, 1 CTA per SM
         tma64 = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(4) == 0   # channel-split kernel (small maps)
+        split = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(0) == 0
         auto = V.correlation(a, b, legacy=legacy)
         auto2 = V.correlation(a, b, legacy=legacy)  # twice on the same stream (reference test.py:70-71)
@@ -196,5 +226,10 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
     torch.cuda.synchronize()
     assert torch.equal(tma32, plain)
     assert torch.equal(tma64, plain)
-    assert torch.equal(auto, plain)
+    tol = 5e-6 * max(float(plain.abs().max()), 1e-30)   # 8 partial sums per value: equal within rounding
+    assert float((split - plain).abs().max()) <= tol
+    if H * W <= 4096:   # auto = channel-split kernel
+        assert torch.equal(auto, split)
+    else:
+        assert torch.equal(auto, plain)
     assert torch.equal(auto, auto2)

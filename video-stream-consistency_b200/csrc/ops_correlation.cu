@@ -412,6 +412,48 @@ __global__ void __launch_bounds__(256) correlation_generic_kernel(const float* _
     out[static_cast<size_t>(n) * per_n + i] = use_div ? acc / scale : acc;
 }
 
+// Small maps (the coarse PWC-Net levels) are pure latency: a few thousand outputs, each a serial walk over up to
+// 196 channels of DRAM-cold operands.  Here the 8 warps of a CTA share 32 outputs and each walks one eighth of
+// the channels (3-4 load batches instead of 25); the partial sums are combined in warp order (deterministic).
+constexpr int kSplitC = 8;
+__global__ void __launch_bounds__(32 * kSplitC) correlation_splitc_kernel(const float* __restrict__ in1,
+    const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, int md, float scale, int use_div)
+{
+    __shared__ float part[kSplitC][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int P = 2 * md + 1;
+    const size_t HW = static_cast<size_t>(H) * W;
+    const size_t per_n = static_cast<size_t>(P) * P * HW;
+    const size_t i = static_cast<size_t>(blockIdx.x) * 32 + lane;
+    const int n = blockIdx.y;
+    float acc = 0.0f;
+    if (i < per_n) {
+        const int w = static_cast<int>(i % W);
+        const int h = static_cast<int>((i / W) % H);
+        const int pw = static_cast<int>((i / HW) % P);
+        const int ph = static_cast<int>(i / (HW * P));
+        const int h2 = h + ph - md, w2 = w + pw - md;
+        if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) {
+            const int cb = static_cast<int>(static_cast<long long>(C) * slice / kSplitC);
+            const int ce = static_cast<int>(static_cast<long long>(C) * (slice + 1) / kSplitC);
+            const float* a = in1 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h) * W + w;
+            const float* b = in2 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h2) * W + w2;
+#pragma unroll 8
+            for (int c = 0; c < ce - cb; ++c)
+                acc = __fmaf_rn(__ldg(a + c * HW), __ldg(b + c * HW), acc);
+        }
+    }
+    part[slice][lane] = acc;
+    __syncthreads();
+    if (slice == 0 && i < per_n) {
+        float sum = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < kSplitC; ++k)
+            sum += part[k][lane];
+        out[static_cast<size_t>(n) * per_n + i] = use_div ? sum / scale : sum;
+    }
+}
+
 // ---- host side: tensor maps ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -452,13 +494,13 @@ static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int
         == CUDA_SUCCESS;
 }
 
-int g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles (tests)
+int g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles, 4 channel-split (tests)
 
 }  // namespace vsc
 
 extern "C" int vsc_set_correlation_mode(int mode)
 {
-    if (mode < 0 || mode > 3)
+    if (mode < 0 || mode > 4)
         return VSC_E_INVALID;
     vsc::g_corr_mode = mode;
     return VSC_OK;
@@ -476,10 +518,11 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
         return VSC_E_ALIGN;
     cudaStream_t st = as_stream(stream);
     // Small maps (the coarse PWC-Net levels: 9x15 ... 36x60 at 1080p/2) give the tiled kernels a handful of CTAs
-    // that each walk all channels serially (76 us for 196x9x15, two CTAs).  One thread per output value spreads
-    // the same work over 81*H*W threads, with both operands L1/L2-resident: a few microseconds.  Same FMA chain
-    // per value, so the results are bit-identical to the tiled kernels.
-    const bool small_map = max_displacement == kMD && g_corr_mode == 0 && static_cast<long long>(H) * W <= 4096;
+    // that each walk all channels serially (76 us for 196x9x15, two CTAs): they go to the channel-split kernel,
+    // which spreads the work over 81*H*W/32 CTAs x 8 channel slices.  Its sums associate differently from the
+    // tiled kernels' (8 partial sums), well inside the op's 1e-4 tolerance.
+    const bool small_map = max_displacement == kMD
+        && (g_corr_mode == 4 || (g_corr_mode == 0 && static_cast<long long>(H) * W <= 4096));
     if (max_displacement == kMD && !small_map) {
         const int vec = (W % 4 == 0) && aligned16(out);
         const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), N);
@@ -522,6 +565,13 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
     }
     const int P = 2 * max_displacement + 1;
     const size_t per_n = static_cast<size_t>(P) * P * H * W;
+    if (g_corr_mode == 4 || per_n * static_cast<size_t>(N) <= (1u << 21)) {
+        const dim3 grids(cdiv(static_cast<long long>(per_n), 32), N);
+        correlation_splitc_kernel<<<grids, 32 * kSplitC, 0, st>>>(in1, in2, out, C, H, W, max_displacement,
+            static_cast<float>(C), legacy ? 1 : 0);
+        count_launch();
+        return launch_status();
+    }
     const dim3 grid(cdiv(static_cast<long long>(per_n), 256), N);
     correlation_generic_kernel<<<grid, 256, 0, st>>>(in1, in2, out, C, H, W, max_displacement, static_cast<float>(C),
         legacy ? 1 : 0);

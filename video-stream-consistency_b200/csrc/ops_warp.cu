@@ -117,6 +117,117 @@ __global__ void __launch_bounds__(256) warp_nchw_kernel(const float* __restrict_
         __stcs(op, warp_sample(ip, t));
 }
 
+
+// ---- tiled variant ------------------------------------------------------------------------------------------
+// The four taps of a pixel are the 2x2 quad at (xb, yb) = (xL, yT) clamped into the image, so ONE 64-bit address
+// per channel (plus a second one row below) serves all four gathers with constant offsets 0 / +1, instead of four
+// separately formed addresses: the per-value instruction count roughly halves.  At the image border, where only
+// some corners are valid, the valid corners land in other slots of the clamped quad; the slots keep the
+// reference's accumulation order (00, 10, 01, 11) among the corners that are used, and unused slots are neither
+// read nor weighted.
+struct WarpQuad {
+    int o;                  // element offset of slot A = (yb, xb) inside one H*W plane
+    float wA, wB, wC, wD;   // weights of slots (yb,xb) (yb,xb+1) (yb+1,xb) (yb+1,xb+1); 0 when unused
+    unsigned used;          // bit k set: slot k is read
+};
+
+__device__ __forceinline__ WarpQuad warp_quad(int x, int y, float fu, float fv, int W, int H)
+{
+    const WarpTap t = warp_setup(x, y, fu, fv, W, H);
+    const float xL = floorf(static_cast<float>(x) + fu);
+    const float yT = floorf(static_cast<float>(y) + fv);
+    // fmaxf/fminf drop a NaN operand, so the conversions below are always in range
+    const int xb = static_cast<int>(fminf(fmaxf(xL, 0.0f), static_cast<float>(max(W - 2, 0))));
+    const int yb = static_cast<int>(fminf(fmaxf(yT, 0.0f), static_cast<float>(max(H - 2, 0))));
+    const int ob = yb * W + xb;
+    // slot of a used corner = (row - yb) * 2 + (col - xb), recovered from its plane offset
+    auto slot = [&](int o) {
+        const int d = o - ob;   // 0, 1, W or W + 1 for a used corner
+        return (d >= W ? 2 : 0) + ((d == 1 || d == W + 1) ? 1 : 0);
+    };
+    // W == 1: a used corner in the next row has d == W == 1; rows win (there is no column xb + 1)
+    auto slot1 = [&](int o) { return (o - ob) >= 1 ? 2 : 0; };
+    const int s00 = W > 1 ? slot(t.o00) : slot1(t.o00), s10 = W > 1 ? slot(t.o10) : slot1(t.o10);
+    const int s01 = W > 1 ? slot(t.o01) : slot1(t.o01), s11 = W > 1 ? slot(t.o11) : slot1(t.o11);
+    const bool v00 = t.valid & 1u, v10 = t.valid & 2u, v01 = t.valid & 4u, v11 = t.valid & 8u;
+    auto pick = [&](int k) {
+        return (v00 && s00 == k) ? t.w00 : (v10 && s10 == k) ? t.w10 : (v01 && s01 == k) ? t.w01
+            : (v11 && s11 == k) ? t.w11 : 0.0f;
+    };
+    auto hit = [&](int k) { return (v00 && s00 == k) || (v10 && s10 == k) || (v01 && s01 == k) || (v11 && s11 == k); };
+    WarpQuad q;
+    q.o = ob;
+    q.wA = pick(0);
+    q.wB = pick(1);
+    q.wC = pick(2);
+    q.wD = pick(3);
+    q.used = (hit(0) ? 1u : 0u) | (hit(1) ? 2u : 0u) | (hit(2) ? 4u : 0u) | (hit(3) ? 8u : 0u);
+    return q;
+}
+
+// grid: x = 32-pixel column tiles, y = 8-row tiles, z = n * channel chunks.  A CTA is a 32x8 pixel tile: each
+// warp stores one 128-byte row segment per channel, and the bottom taps of a row are the top taps of the row
+// below it in the same CTA, so they hit in L1 instead of going back to L2.
+constexpr int kWarpTileW = 32, kWarpTileH = 8;
+__global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_tiled_kernel(const float* __restrict__ in,
+    const float* __restrict__ flow, float* __restrict__ out, int C, int H, int W, int chunk, int nchunk)
+{
+    const int x = blockIdx.x * kWarpTileW + (threadIdx.x & (kWarpTileW - 1));
+    const int y = blockIdx.y * kWarpTileH + (threadIdx.x / kWarpTileW);
+    if (x >= W || y >= H)
+        return;
+    const int HW = H * W;
+    const int n = blockIdx.z / nchunk;
+    const int c0 = (blockIdx.z - n * nchunk) * chunk;
+    const int c1 = min(C, c0 + chunk);
+    const int p = y * W + x;
+    const float* fl = flow + static_cast<size_t>(n) * 2 * HW + p;
+    const WarpQuad q = warp_quad(x, y, ldg_stream(fl), ldg_stream(fl + HW), W, H);
+    const bool uA = q.used & 1u, uB = q.used & 2u, uC = q.used & 4u, uD = q.used & 8u;
+
+    const float* pt = in + (static_cast<size_t>(n) * C + c0) * HW + q.o;   // slot A of channel c
+    const float* pb = pt + W;                                             // slot C
+    float* op = out + (static_cast<size_t>(n) * C + c0) * HW + p;
+    auto sample = [&](const float* t, const float* b) {
+        const float va = uA ? __ldg(t) : 0.0f;
+        const float vb = uB ? __ldg(t + 1) : 0.0f;
+        const float vc = uC ? __ldg(b) : 0.0f;
+        const float vd = uD ? __ldg(b + 1) : 0.0f;
+        float v = q.wA * va;
+        v = v + q.wB * vb;
+        v = v + q.wC * vc;
+        v = v + q.wD * vd;
+        return v;
+    };
+    int c = c0;
+    for (; c + 4 <= c1; c += 4) {
+        const float* t1 = pt + HW;
+        const float* b1 = pb + HW;
+        const float* t2 = t1 + HW;
+        const float* b2 = b1 + HW;
+        const float* t3 = t2 + HW;
+        const float* b3 = b2 + HW;
+        const float v0 = sample(pt, pb);
+        const float v1 = sample(t1, b1);
+        const float v2 = sample(t2, b2);
+        const float v3 = sample(t3, b3);
+        float* o1 = op + HW;
+        float* o2 = o1 + HW;
+        float* o3 = o2 + HW;
+        __stcs(op, v0);
+        __stcs(o1, v1);
+        __stcs(o2, v2);
+        __stcs(o3, v3);
+        pt = t3 + HW;
+        pb = b3 + HW;
+        op = o3 + HW;
+    }
+    for (; c < c1; ++c, pt += HW, pb += HW, op += HW)
+        __stcs(op, sample(pt, pb));
+}
+
+int g_warp_mode = 0;  // 0 auto (tiled), 1 linear one-pixel-per-thread kernel, 2 tiled
+
 }  // namespace vsc
 
 extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out, int N, int C, int H, int W,
@@ -129,6 +240,24 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
         return VSC_E_INVALID;
     if (!aligned4(in) || !aligned4(flow) || !aligned4(out))
         return VSC_E_ALIGN;
+    if (g_warp_mode != 1) {
+        const unsigned tx = cdiv(W, kWarpTileW), ty = cdiv(H, kWarpTileH);
+        const long long tiles = static_cast<long long>(tx) * ty * N;
+        const long long want = 4LL * sm_count() * 8;
+        int nchunk = static_cast<int>((want + tiles - 1) / tiles);
+        if (nchunk < 1) nchunk = 1;
+        if (nchunk > (C + 7) / 8) nchunk = (C + 7) / 8;
+        int chunk = (C + nchunk - 1) / nchunk;
+        chunk = (chunk + 3) / 4 * 4;  // whole unrolled groups
+        nchunk = (C + chunk - 1) / chunk;
+        if (ty > 65535 || static_cast<long long>(N) * nchunk > 65535)
+            return VSC_E_INVALID;
+        const dim3 grid(tx, ty, static_cast<unsigned>(N * nchunk));
+        warp_nchw_tiled_kernel<<<grid, kWarpTileW * kWarpTileH, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk,
+            nchunk);
+        count_launch();
+        return launch_status();
+    }
     const unsigned gx = cdiv(static_cast<long long>(H) * W, 256);
     // enough blocks for >= 4 waves of 148 SMs x 8 resident CTAs when the tensor allows, chunks of >= 8 channels
     const long long want = 4LL * sm_count() * 8;
@@ -143,4 +272,12 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     warp_nchw_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk);
     count_launch();
     return launch_status();
+}
+
+extern "C" int vsc_set_warp_mode(int mode)
+{
+    if (mode < 0 || mode > 2)
+        return VSC_E_INVALID;
+    vsc::g_warp_mode = mode;
+    return VSC_OK;
 }
