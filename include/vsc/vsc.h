@@ -82,7 +82,7 @@ VSC_API int vsc_correlation_f32(const float* in1, const float* in2, float* out, 
 /* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases; 64x8 tiles
  * for W >= 96, else 32x8), plain loads otherwise;  1: always the plain-load stager;  2 / 3: TMA with 32x8 / 64x8
  * tiles -- same arithmetic, bit-identical results;  4: the channel-split kernel that mode 0 uses for maps of at
- * most 4096 pixels (8 partial sums per value: equal within rounding).  For tests. */
+ * most 12288 pixels (8 partial sums per value: equal within rounding).  For tests. */
 VSC_API int vsc_set_correlation_mode(int mode);
 
 /* custom::Warp: masked bilinear backward warp (warp.cc:71-134 / warp_cuda.cu:29-84).
@@ -127,8 +127,8 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  *   1  unblocked sweeps only;   2  blocked passes whenever numIter >= 4, whatever the image size.
  * Two flag bits select variants of the blocked kernel (same results): | 0x10 = CTA-wide barrier instead of
  * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging;
- * | 0x40 = vsc_frame_stabilize never takes its fused path; | (k << 8), k = 1..5, forces the band geometry of the
- * blocked kernel (512, 448, 384, 256 floats at one CTA per SM, 256 floats at two CTAs per SM) instead of the cost model.
+ * | 0x40 = vsc_frame_stabilize never takes its fused path; | (k << 8), k = 1..4, forces the band width of the
+ * blocked kernel (512, 448, 384, 256 floats) instead of the cost model.
  * Process-wide; meant for tests and benchmarks. */
 VSC_API int vsc_set_solver_mode(int mode);
 

@@ -21,7 +21,7 @@ dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
 g = torch.Generator(device=dev).manual_seed(0)
 L = V.lib()
-NAMES = {0: "auto", 1: "512x1", 2: "448x1", 3: "384x1", 4: "256x1", 5: "256x2"}
+NAMES = {0: "auto", 1: "512", 2: "448", 3: "384", 4: "256"}
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 
 
@@ -43,7 +43,7 @@ for (W, H) in ((3840, 2160), (1920, 1080), (1280, 720), (960, 540), (640, 360)):
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
     out = pr.clone()
     row = []
-    for k in range(0, 6):
+    for k in range(0, 5):
         V.check(L.vsc_set_solver_mode(2 | (k << 8)))
         time_solve(pr, tg, wt, out, T * 4, reps=2)
         a = time_solve(pr, tg, wt, out, T * 4)

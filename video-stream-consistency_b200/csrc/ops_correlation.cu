@@ -412,45 +412,75 @@ __global__ void __launch_bounds__(256) correlation_generic_kernel(const float* _
     out[static_cast<size_t>(n) * per_n + i] = use_div ? acc / scale : acc;
 }
 
-// Small maps (the coarse PWC-Net levels) are pure latency: a few thousand outputs, each a serial walk over up to
-// 196 channels of DRAM-cold operands.  Here the 8 warps of a CTA share 32 outputs and each walks one eighth of
-// the channels (3-4 load batches instead of 25); the partial sums are combined in warp order (deterministic).
-constexpr int kSplitC = 8;
-__global__ void __launch_bounds__(32 * kSplitC) correlation_splitc_kernel(const float* __restrict__ in1,
-    const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, int md, float scale, int use_div)
+// Small maps (the coarse PWC-Net levels) are pure latency: a few thousand pixels, each output a serial walk over
+// up to 196 channels of DRAM-cold operands, and the tiled kernels above get only a handful of CTAs.  Here a
+// thread owns one (ph, h, w) task = the 9 horizontal displacements of one pixel and one vertical displacement:
+// per channel it loads in1 once and 9 neighbouring in2 values (1.1 loads per FMA instead of 2; lanes are
+// consecutive w, so every load is a contiguous row segment).  The 8 warps of a CTA share 32 tasks and each walks
+// one eighth of the channels (2-4 load batches instead of 25); the 8 partial sums of a value are combined in
+// warp order through shared memory (deterministic).
+// (kSplitC = 16 for the very smallest maps, whose grids do not even fill the SMs at 8.)
+template <int kSplitC>
+__global__ void __launch_bounds__(32 * kSplitC) correlation_md4_rows_kernel(const float* __restrict__ in1,
+    const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float scale, int use_div)
 {
-    __shared__ float part[kSplitC][32];
+    __shared__ float part[kSplitC][kP][32];
+    __shared__ int obase[32];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const int P = 2 * md + 1;
-    const size_t HW = static_cast<size_t>(H) * W;
-    const size_t per_n = static_cast<size_t>(P) * P * HW;
-    const size_t i = static_cast<size_t>(blockIdx.x) * 32 + lane;
+    const unsigned HW = static_cast<unsigned>(H) * W;
+    const unsigned tasks = kP * HW;                       // per n: (ph, h, w), w fastest
+    const unsigned i = blockIdx.x * 32u + lane;
     const int n = blockIdx.y;
-    float acc = 0.0f;
-    if (i < per_n) {
-        const int w = static_cast<int>(i % W);
-        const int h = static_cast<int>((i / W) % H);
-        const int pw = static_cast<int>((i / HW) % P);
-        const int ph = static_cast<int>(i / (HW * P));
-        const int h2 = h + ph - md, w2 = w + pw - md;
-        if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) {
+    float acc[kP];
+#pragma unroll
+    for (int j = 0; j < kP; ++j)
+        acc[j] = 0.0f;
+    int ob = -1;
+    if (i < tasks) {
+        const unsigned ph = i / HW;
+        const unsigned hw = i - ph * HW;
+        const int h = static_cast<int>(hw / W);
+        const int w = static_cast<int>(hw - static_cast<unsigned>(h) * W);
+        ob = static_cast<int>(ph * kP * HW + hw);        // + pw * HW
+        const int h2 = h + static_cast<int>(ph) - kMD;
+        if (h2 >= 0 && h2 < H) {
+            unsigned colmask = 0;
+#pragma unroll
+            for (int j = 0; j < kP; ++j)
+                colmask |= (w + j - kMD >= 0 && w + j - kMD < W) ? (1u << j) : 0u;
             const int cb = static_cast<int>(static_cast<long long>(C) * slice / kSplitC);
             const int ce = static_cast<int>(static_cast<long long>(C) * (slice + 1) / kSplitC);
-            const float* a = in1 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h) * W + w;
-            const float* b = in2 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h2) * W + w2;
-#pragma unroll 8
-            for (int c = 0; c < ce - cb; ++c)
-                acc = __fmaf_rn(__ldg(a + c * HW), __ldg(b + c * HW), acc);
+            const float* a = in1 + (static_cast<size_t>(n) * C + cb) * HW + hw;
+            // column w-4 of row h2; lanes whose left columns fall outside the row never dereference them
+            const float* b = in2 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h2) * W + w - kMD;
+#pragma unroll 4
+            for (int c = 0; c < ce - cb; ++c, a += HW, b += HW) {
+                const float av = __ldg(a);
+#pragma unroll
+                for (int j = 0; j < kP; ++j) {
+                    const float bv = (colmask >> j) & 1u ? __ldg(b + j) : 0.0f;
+                    acc[j] = __fmaf_rn(av, bv, acc[j]);
+                }
+            }
         }
     }
-    part[slice][lane] = acc;
-    __syncthreads();
-    if (slice == 0 && i < per_n) {
-        float sum = part[0][lane];
 #pragma unroll
-        for (int k = 1; k < kSplitC; ++k)
-            sum += part[k][lane];
-        out[static_cast<size_t>(n) * per_n + i] = use_div ? sum / scale : sum;
+    for (int j = 0; j < kP; ++j)
+        part[slice][j][lane] = acc[j];
+    if (slice == 0)
+        obase[lane] = ob;
+    __syncthreads();
+    // 9 x 32 values per CTA: warp k sums displacement k (and k + kSplitC); 128-byte row stores
+    for (int j = slice; j < kP; j += kSplitC) {
+        const int o = obase[lane];
+        if (o >= 0) {
+            float sum = part[0][j][lane];
+#pragma unroll
+            for (int k = 1; k < kSplitC; ++k)
+                sum += part[k][j][lane];
+            out[static_cast<size_t>(n) * kP * tasks + static_cast<unsigned>(o) + static_cast<size_t>(j) * HW]
+                = use_div ? sum / scale : sum;
+        }
     }
 }
 
@@ -518,11 +548,11 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
         return VSC_E_ALIGN;
     cudaStream_t st = as_stream(stream);
     // Small maps (the coarse PWC-Net levels: 9x15 ... 36x60 at 1080p/2) give the tiled kernels a handful of CTAs
-    // that each walk all channels serially (76 us for 196x9x15, two CTAs): they go to the channel-split kernel,
-    // which spreads the work over 81*H*W/32 CTAs x 8 channel slices.  Its sums associate differently from the
-    // tiled kernels' (8 partial sums), well inside the op's 1e-4 tolerance.
+    // that each walk all channels serially (76 us for 196x9x15, two CTAs): they go to the channel-split rows
+    // kernel, which spreads the work over 9*H*W/32 CTAs x 8 channel slices.  Its sums associate differently
+    // from the tiled kernels' (8 partial sums), well inside the op's 1e-4 tolerance.
     const bool small_map = max_displacement == kMD
-        && (g_corr_mode == 4 || (g_corr_mode == 0 && static_cast<long long>(H) * W <= 4096));
+        && (g_corr_mode == 4 || (g_corr_mode == 0 && static_cast<long long>(H) * W <= 12288));
     if (max_displacement == kMD && !small_map) {
         const int vec = (W % 4 == 0) && aligned16(out);
         const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), N);
@@ -565,10 +595,14 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
     }
     const int P = 2 * max_displacement + 1;
     const size_t per_n = static_cast<size_t>(P) * P * H * W;
-    if (g_corr_mode == 4 || per_n * static_cast<size_t>(N) <= (1u << 21)) {
-        const dim3 grids(cdiv(static_cast<long long>(per_n), 32), N);
-        correlation_splitc_kernel<<<grids, 32 * kSplitC, 0, st>>>(in1, in2, out, C, H, W, max_displacement,
-            static_cast<float>(C), legacy ? 1 : 0);
+    if (max_displacement == kMD && static_cast<long long>(H) * W * kP * kP < 0x7fffffffLL) {
+        const dim3 grids(cdiv(static_cast<long long>(kP) * H * W, 32), N);
+        if (static_cast<long long>(grids.x) * N < 2LL * sm_count() && C >= 64)
+            correlation_md4_rows_kernel<16><<<grids, 32 * 16, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
+                legacy ? 1 : 0);
+        else
+            correlation_md4_rows_kernel<8><<<grids, 32 * 8, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
+                legacy ? 1 : 0);
         count_launch();
         return launch_status();
     }

@@ -269,7 +269,7 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 
 extern "C" int vsc_set_solver_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x7FF || (mode & 0x80) || ((mode >> 8) & 7) > 5)
+    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x7FF || (mode & 0x80) || ((mode >> 8) & 7) > 4)
         return VSC_E_INVALID;
     g_solver_mode = mode & 0xF;
     g_stream_pair = (mode & 0x10) == 0;

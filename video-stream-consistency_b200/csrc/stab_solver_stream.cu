@@ -37,15 +37,16 @@ __host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 :
 __host__ __device__ constexpr int stream_halo(int T) { return (3 * T + 3) / 4 * 4; }
 bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
 bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
-int g_stream_band = 0;              // 0 = cost model; 1..5 force a band candidate (benchmarks, vsc_set_solver_mode)
+int g_stream_band = 0;              // 0 = cost model; 1..4 force a band candidate (benchmarks, vsc_set_solver_mode)
 
-// BW = band width in floats = threads per CTA; OCC = CTAs resident per SM (1, or 2 for the 256-wide band: small
-// images are latency-bound per step, so two independent CTAs per SM halve the steps at little cost per step)
+// BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best.
+// Two 256-wide CTAs per SM were measured slower than every single-CTA geometry at every size from 640x360 to
+// 4K -- profiles/r1_sweep_bands.txt -- and are not built)
 // COOP: level-0 rows staged warp-cooperatively with 16-byte cp.async (one chunk per lane and row; needs
 // 3W % 4 == 0 and 16-byte aligned images); otherwise every thread stages its own four floats (4-byte cp.async).
 // PAIR: the exchange ring is synchronised between neighbouring warps only (named barriers).
-template <int T, int BW, int OCC, bool COOP, bool PAIR>
-__global__ void __launch_bounds__(BW, OCC) solver_stream_kernel(const float* __restrict__ coefA,
+template <int T, int BW, bool COOP, bool PAIR>
+__global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
 {
@@ -277,11 +278,10 @@ struct StreamGeom {
     long long cost;
 };
 
-// grid of one band width: bands x row chunks, at most ONE wave (a grid of slots+1 CTAs takes twice as long as a
-// grid of `slots` = SMs x CTAs-per-SM); cost ~ per-SM time = steps x resident warps
-static StreamGeom stream_geom(int T, int BW, int occ, int L, int H, int sm_n)
+// grid of one band width: bands x row chunks, at most ONE wave (1 CTA per SM: a grid of sms+1 CTAs takes twice
+// as long as a grid of sms CTAs); cost ~ per-SM time = steps x warps
+static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
 {
-    const int sms = sm_n * occ;
     StreamGeom g;
     const int S = BW - 2 * stream_halo(T);
     g.nb = (L + S - 1) / S;
@@ -293,38 +293,38 @@ static StreamGeom stream_geom(int T, int BW, int occ, int L, int H, int sm_n)
     g.chunk_rows = (H + nc - 1) / nc;
     g.nc = (H + g.chunk_rows - 1) / g.chunk_rows;
     const long long waves = (static_cast<long long>(g.nb) * g.nc + sms - 1) / sms;
-    g.cost = waves * (g.chunk_rows + 3 * T) * BW * occ;
+    g.cost = waves * (g.chunk_rows + 3 * T) * BW;
     return g;
 }
 
-template <int T, int BW, int OCC, bool COOP, bool PAIR>
+template <int T, int BW, bool COOP, bool PAIR>
 static int launch_stream_impl(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     constexpr int PF = COOP ? 2 * T : stream_private_pf(T);
     const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static unsigned long long configured = 0;
-    if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, OCC, COOP, PAIR>, smem, OCC > 1, configured))
+    if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, COOP, PAIR>, smem, false, configured))
         return e;
     const dim3 grid(g.nb, g.nc);
-    solver_stream_kernel<T, BW, OCC, COOP, PAIR><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
+    solver_stream_kernel<T, BW, COOP, PAIR><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
         step, mom);
     count_launch();
     return launch_status();
 }
 
-template <int T, int BW, int OCC>
+template <int T, int BW>
 static int launch_stream(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     const bool coop = (3LL * W) % 4 == 0 && aligned16(coefA) && aligned16(coefB) && aligned16(u_src) && aligned16(o_src)
         && g_stream_coop;
     if (coop && g_stream_pair)
-        return launch_stream_impl<T, BW, OCC, true, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        return launch_stream_impl<T, BW, true, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (coop)
-        return launch_stream_impl<T, BW, OCC, true, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom,
+        return launch_stream_impl<T, BW, true, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom,
             st);
-    return launch_stream_impl<T, BW, OCC, false, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    return launch_stream_impl<T, BW, false, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
 }
 
 template <int T>
@@ -332,17 +332,16 @@ static int launch_stream_best(const float* coefA, const float* coefB, const floa
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     const int L = 3 * W, sms = sm_count();
-    constexpr int NCAND = 5;
-    const int cands[NCAND] = {512, 448, 384, 256, 256};
-    const int occs[NCAND] = {1, 1, 1, 1, 2};
+    constexpr int NCAND = 4;
+    const int cands[NCAND] = {512, 448, 384, 256};
     int best = 0;
-    StreamGeom bg = stream_geom(T, cands[0], occs[0], L, H, sms);
+    StreamGeom bg = stream_geom(T, cands[0], L, H, sms);
     if (g_stream_band >= 1 && g_stream_band <= NCAND) {
         best = g_stream_band - 1;
-        bg = stream_geom(T, cands[best], occs[best], L, H, sms);
+        bg = stream_geom(T, cands[best], L, H, sms);
     } else {
         for (int i = 1; i < NCAND; ++i) {
-            const StreamGeom g = stream_geom(T, cands[i], occs[i], L, H, sms);
+            const StreamGeom g = stream_geom(T, cands[i], L, H, sms);
             if (g.cost < bg.cost) {
                 bg = g;
                 best = i;
@@ -350,11 +349,10 @@ static int launch_stream_best(const float* coefA, const float* coefB, const floa
         }
     }
     switch (best) {
-        case 0: return launch_stream<T, 512, 1>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-        case 1: return launch_stream<T, 448, 1>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-        case 2: return launch_stream<T, 384, 1>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-        case 3: return launch_stream<T, 256, 1>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-        default: return launch_stream<T, 256, 2>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        case 0: return launch_stream<T, 512>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        case 1: return launch_stream<T, 448>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        case 2: return launch_stream<T, 384>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        default: return launch_stream<T, 256>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     }
 }
 
