@@ -56,7 +56,17 @@ enum {
     VSC_E_INVALID = -1,   /* null pointer / non-positive size / unsupported channel count */
     VSC_E_WORKSPACE = -2, /* workspace missing or too small */
     VSC_E_STATE = -3,     /* stabilizer called out of order (e.g. step before 3 frames were pushed) */
-    VSC_E_ALIGN = -4      /* pointer not aligned to 4 bytes */
+    VSC_E_ALIGN = -4,     /* pointer not aligned to 4 bytes */
+    /* .flo ingestion: one code per exception of the reference's ReadFlowFile (flowIO.cpp:31-78) and
+     * initializeFlowImage (imagehelpers.cpp:42-50); vsc_error_string() returns the reference's message */
+    VSC_E_FLO_OPEN = -5,    /* "ReadFlowFile: could not open" */
+    VSC_E_FLO_HEADER = -6,  /* "ReadFlowFile: problem reading file" */
+    VSC_E_FLO_TAG = -7,     /* "ReadFlowFile: wrong tag (possibly due to big-endian machine?)" */
+    VSC_E_FLO_WIDTH = -8,   /* "ReadFlowFile: illegal width" */
+    VSC_E_FLO_HEIGHT = -9,  /* "ReadFlowFile: illegal height" */
+    VSC_E_FLO_SHORT = -10,  /* "ReadFlowFile: file is too short" */
+    VSC_E_FLO_LONG = -11,   /* "ReadFlowFile: file is too long" */
+    VSC_E_FLO_DIMS = -12    /* "Flow image size does not match image size" */
 };
 
 typedef void* vsc_stream_t; /* cudaStream_t */
@@ -215,6 +225,12 @@ VSC_API int vsc_stabilizer_step_lowres_flow(vsc_stabilizer* s, const float* flow
  * through pinned staging), up-sampled like _step_lowres_flow if smaller than the frame. */
 VSC_API int vsc_stabilizer_step_host_flow(vsc_stabilizer* s, const float* flowFwd_host, const float* flowBwd_host,
     int flowW, int flowH, uint8_t* out_rgba_host);
+/* same, flows read from <flow_dir>/frame_%06d.flo (currentFrame + 1: previous -> current ... see
+ * stabilizefiles.cpp:139-144) and <flow_dir>/frame_%06d_bwd.flo (currentFrame): what
+ * FileStabilizer::retrieveOpticalFlow + doOneStep do for frame `currentFrame`.  The stabilizer must have been
+ * created with flow_channels == 2; files of another size than the frame fail with VSC_E_FLO_DIMS. */
+VSC_API int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame,
+    uint8_t* out_rgba_host);
 VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
 /* device pointer to the fp32 result of the last step (W*H*3 floats), for tests */
 VSC_API const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s);
@@ -223,6 +239,16 @@ VSC_API int vsc_stabilizer_copy_last_output(vsc_stabilizer* s, float* dst_dev);
 VSC_API vsc_stream_t vsc_stabilizer_compute_stream(vsc_stabilizer* s);
 /* clears the window and the recurrence (seek) */
 VSC_API int vsc_stabilizer_reset(vsc_stabilizer* s);
+
+/* ---- .flo ingestion (host side; precomputed-flow mode) -------------------------------------------------
+ * vsc_flo_read: ReadFlowFile (flowIO.cpp:31-78) into a caller buffer of dst_capacity_floats floats (use
+ * vsc_host_alloc memory to make the following upload asynchronous); *width / *height receive the header
+ * values.  A buffer smaller than width*height*2 fails with VSC_E_WORKSPACE after the header was read, so a
+ * caller may size the buffer from vsc_flo_read_header.  Errors: VSC_E_FLO_*, one per reference exception.
+ * vsc_flo_frame_path: "<dir>/frame_%06d.flo" or "<dir>/frame_%06d_bwd.flo" (stabilizefiles.cpp:99-101,141-144). */
+VSC_API int vsc_flo_read_header(const char* path, int* width, int* height);
+VSC_API int vsc_flo_read(const char* path, float* dst, size_t dst_capacity_floats, int* width, int* height);
+VSC_API int vsc_flo_frame_path(const char* flow_dir, int frame, int backward, char* out, size_t out_capacity);
 
 /* pinned host memory for frame buffers (cudaHostAlloc / cudaFreeHost) */
 VSC_API int vsc_host_alloc(void** p, size_t bytes);

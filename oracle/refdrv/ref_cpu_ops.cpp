@@ -141,6 +141,23 @@ int vsc_ref_read_flo(const char* path, float* buf, size_t cap_floats, int* w, in
     }
 }
 
+// same, returning the reference's exception text
+int vsc_ref_read_flo_msg(const char* path, float* buf, size_t cap_floats, int* w, int* h, char* msg, size_t msg_cap)
+{
+    try {
+        std::vector<float> flow;
+        ReadFlowFile(flow, *w, *h, path);
+        if (flow.size() > cap_floats)
+            return 2;
+        std::memcpy(buf, flow.data(), flow.size() * sizeof(float));
+        return 0;
+    } catch (const std::exception& e) {
+        if (msg && msg_cap)
+            std::snprintf(msg, msg_cap, "%s", e.what());
+        return 1;
+    }
+}
+
 int vsc_ref_write_flo(const char* path, const float* buf, int w, int h)
 {
     try {

@@ -36,6 +36,7 @@ def build_host_shims(force: bool = False):
     if os.path.exists(os.path.join(REF_STAB, "flowconsistency.cuh")):
         jobs.append((os.path.join(TEST_SO_DIR, "libvsc_stab_shim_test.so"),
                      [os.path.join(HERE, "host", "stabilization", "vsc_flowconsistency.cpp"),
+                      os.path.join(HERE, "host", "stabilization", "vsc_flowio.cpp"),
                       os.path.join(ROOT, "tests", "cxx", "stab_shim_driver.cpp")],
                      ["-I", REF_STAB, "-I", os.path.join(ROOT, "standins", "qt"), "-I", CUDA_INC],
                      ["-lvsc_b200", "-L", CUDA_LIB, f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"]))

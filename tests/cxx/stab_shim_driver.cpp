@@ -3,6 +3,7 @@
 // frames through GPUImage::copyFromQImage, and runs the doOneStep call sequence (videostabilizer.cpp:177-247)
 // through the six flowconsistency.cuh functions, which here resolve to the shim (i.e. to libvsc_b200.so).
 // Compiled against the reference's unmodified gpuimage.h / flowconsistency.cuh and the QImage stand-in.
+#include "flowIO.h"
 #include "flowconsistency.cuh"
 #include "gpuimage.h"
 
@@ -26,6 +27,23 @@ std::unique_ptr<GPUImage> mk(int w, int h, int c) { return std::unique_ptr<GPUIm
 }  // namespace
 
 extern "C" {
+
+// ReadFlowFile of the shim (flowIO.h signature): 0 = ok, 1 = it threw (message copied to msg), 2 = buffer too small
+int vsc_shim_read_flo(const char* path, float* buf, size_t cap_floats, int* w, int* h, char* msg, size_t msg_cap)
+{
+    try {
+        std::vector<float> flow;
+        ReadFlowFile(flow, *w, *h, path);
+        if (flow.size() > cap_floats)
+            return 2;
+        std::memcpy(buf, flow.data(), flow.size() * sizeof(float));
+        return 0;
+    } catch (const std::exception& e) {
+        if (msg && msg_cap)
+            std::snprintf(msg, msg_cap, "%s", e.what());
+        return 1;
+    }
+}
 
 void* vsc_shim_create(int W, int H, int flowC, int levels)
 {

@@ -145,6 +145,19 @@ def _oracle_sequence(O, o8, p8, ff, fb, steps, params=None):
     return outs
 
 
+def _oracle_sequence_per_frame_flows(O, o8, p8, flows, params=None):
+    """like _oracle_sequence for steps 1..len(flows), with a different (fwd, bwd) flow pair per frame; -> RGBA8 frames"""
+    of = [O.rgba8_to_f32x3(x) for x in o8]
+    pf = [O.rgba8_to_f32x3(x) for x in p8]
+    last = pf[2]
+    outs = []
+    for i, (ff, fb) in enumerate(flows):
+        t = i + 1
+        last, rgba = O.do_one_step(of[t - 1], of[t], of[t + 1], pf[t - 1], pf[t], pf[t + 1], last, ff, fb, params)
+        outs.append(rgba)
+    return outs
+
+
 @pytest.mark.parametrize("W,H,fc", [(64, 48, 3), (45, 37, 3), (64, 48, 2), (50, 30, 3)])
 def test_stabilizer_sequence_vs_oracle(V, O, dev, W, H, fc):
     """preload + 3 doOneStep calls through the pipeline object with HOST frames (pageable), vs the oracle."""
@@ -452,3 +465,44 @@ def test_precomputed_flow_files_mode(V, O, dev, tmp_path, W, H):
     with pytest.raises(V.VscError):
         st.step_host_flow(ff, fb)   # window not refilled
     st.close()
+
+
+def test_flow_directory_step(V, O, dev, tmp_path):
+    """-f <flowdir> through the pipeline object: vsc_stabilizer_step_flow_files reads frame_%06d.flo /
+    frame_%06d_bwd.flo itself (pinned landing buffers) and equals the host-flow step on the same data; files of
+    another size, missing files and a 3-channel stabilizer are refused without consuming the window."""
+    W, H = 72, 40
+    o8, p8 = synth.frames(W, H, 5, seed=96)
+    flows = [synth.flows(W, H, 2, seed=100 + t) for t in range(3)]
+    d = str(tmp_path)
+    for t, cur in enumerate((1, 2, 3)):   # current frame index `cur`: fwd file cur+1, bwd file cur
+        _write_flo(V.flo_frame_path(d, cur + 1), flows[t][0])
+        _write_flo(V.flo_frame_path(d, cur, backward=True), flows[t][1])
+    ref = _oracle_sequence_per_frame_flows(O, o8, p8, flows, dict(numIter=20))
+    st = V.Stabilizer(W, H, 2)
+    st.hyper_params.numIter = 20
+    for t in range(3):
+        st.push_frame(o8[t], p8[t])
+    outs = [np.zeros((H, W, 4), np.uint8) for _ in range(3)]
+    with pytest.raises(V.VscError, match="could not open"):
+        st.step_flow_files(d, 40, outs[0])
+    other = str(tmp_path / "other")
+    os.makedirs(other)
+    _write_flo(V.flo_frame_path(other, 2), flows[0][0][:, :W - 2])
+    _write_flo(V.flo_frame_path(other, 1, backward=True), flows[0][1][:, :W - 2])
+    with pytest.raises(V.VscError, match="does not match"):
+        st.step_flow_files(other, 1, outs[0])
+    for t, cur in enumerate((1, 2, 3)):   # the refused calls above left the window intact
+        st.step_flow_files(d, cur, outs[t])
+        if t < 2:
+            st.push_frame(o8[3 + t], p8[3 + t])
+    st.sync()
+    for t in range(3):
+        assert np.abs(outs[t].astype(np.int32) - ref[t].astype(np.int32)).max() <= 1, t
+    st.close()
+    st3 = V.Stabilizer(W, H, 3)
+    for t in range(3):
+        st3.push_frame(o8[t], p8[t])
+    with pytest.raises(V.VscError):
+        st3.step_flow_files(d, 1)
+    st3.close()

@@ -394,6 +394,41 @@ extern "C" int vsc_stabilizer_step_host_flow(vsc_stabilizer* s, const float* flo
     return rc;
 }
 
+namespace vsc {
+int flo_read_into(const char* path, float* dst, size_t cap_floats, int* width, int* height);  // flo_io.cu
+}
+
+// FileStabilizer::retrieveOpticalFlow (stabilizefiles.cpp:135-149) + doOneStep: the two .flo files of frame
+// `currentFrame` are read straight into the pinned landing buffers and uploaded on the copy stream.
+extern "C" int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame,
+    uint8_t* out_rgba_host)
+{
+    if (!s || !flow_dir || s->flowC != 2)
+        return VSC_E_INVALID;
+    if (s->count != 3)
+        return VSC_E_STATE;
+    char path[2][4096];
+    int rc;
+    // "flow file i describes i-1 -> i; bwd flow file describes i -> i-1" (stabilizefiles.cpp:139-144)
+    if ((rc = vsc_flo_frame_path(flow_dir, currentFrame + 1, 0, path[0], sizeof(path[0]))))
+        return rc;
+    if ((rc = vsc_flo_frame_path(flow_dir, currentFrame, 1, path[1], sizeof(path[1]))))
+        return rc;
+    if (s->flow_used)
+        cudaEventSynchronize(s->flow_ready);  // previous H2D out of the pinned landing buffers finished
+    for (int i = 0; i < 2; ++i) {
+        int w = 0, h = 0;
+        // a file of another size must not be read into the frame-sized buffer: check the header first
+        if ((rc = vsc_flo_read_header(path[i], &w, &h)))
+            return rc;
+        if (w != s->W || h != s->H)
+            return VSC_E_FLO_DIMS;            // initializeFlowImage, imagehelpers.cpp:45-49
+        if ((rc = vsc::flo_read_into(path[i], s->flowPin[i], s->P * 2, &w, &h)))
+            return rc;
+    }
+    return vsc_stabilizer_step_host_flow(s, s->flowPin[0], s->flowPin[1], s->W, s->H, out_rgba_host);
+}
+
 extern "C" int vsc_stabilizer_sync(vsc_stabilizer* s)
 {
     if (!s)

@@ -38,6 +38,15 @@ extern "C" const char* vsc_error_string(int code)
         case VSC_E_WORKSPACE: return "workspace missing, misaligned or too small";
         case VSC_E_STATE: return "stabilizer called out of order";
         case VSC_E_ALIGN: return "pointer not sufficiently aligned";
+        // the reference's exception texts (flowIO.cpp:35-74, imagehelpers.cpp:48); callers append the file name
+        case VSC_E_FLO_OPEN: return "ReadFlowFile: could not open";
+        case VSC_E_FLO_HEADER: return "ReadFlowFile: problem reading file";
+        case VSC_E_FLO_TAG: return "ReadFlowFile: wrong tag (possibly due to big-endian machine?)";
+        case VSC_E_FLO_WIDTH: return "ReadFlowFile: illegal width";
+        case VSC_E_FLO_HEIGHT: return "ReadFlowFile: illegal height";
+        case VSC_E_FLO_SHORT: return "ReadFlowFile: file is too short";
+        case VSC_E_FLO_LONG: return "ReadFlowFile: file is too long";
+        case VSC_E_FLO_DIMS: return "Flow image size does not match image size";
         default: break;
     }
     if (code > 0)

@@ -300,6 +300,13 @@ class Stabilizer:
         outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
         check(lib().vsc_stabilizer_step_host_flow(self._h, pf, pb, fw, fh, outp))
 
+    def step_flow_files(self, flow_dir: str, current_frame: int, out_rgba_host=None):
+        """doOneStep of the file mode (-f <flowdir>): reads <flow_dir>/frame_%06d.flo (current_frame + 1) and
+        frame_%06d_bwd.flo (current_frame) like FileStabilizer::retrieveOpticalFlow, then steps."""
+        outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
+        check(lib().vsc_stabilizer_step_flow_files(self._h, os.fsencode(flow_dir), int(current_frame), outp),
+              os.fspath(flow_dir))
+
     def sync(self):
         check(lib().vsc_stabilizer_sync(self._h))
 
@@ -317,3 +324,23 @@ class Stabilizer:
         check(lib().vsc_stabilizer_copy_last_output(self._h, C.c_void_p(out.data_ptr())))
         self.sync()
         return out
+
+
+# ------------------------------------------------------------------ .flo ingestion (host side)
+def flo_frame_path(flow_dir: str, frame: int, backward: bool = False) -> str:
+    """<flow_dir>/frame_%06d.flo or frame_%06d_bwd.flo (stabilizefiles.cpp:141-144)."""
+    buf = C.create_string_buffer(4096)
+    check(lib().vsc_flo_frame_path(os.fsencode(flow_dir), int(frame), 1 if backward else 0, buf, len(buf)))
+    return os.fsdecode(buf.value)
+
+
+def flo_read(path: str, pinned: bool = False) -> torch.Tensor:
+    """ReadFlowFile (flowIO.cpp:31-78): -> float32 HOST tensor [H,W,2]; raises VscError with the reference's
+    message on the reference's error conditions."""
+    w, h = C.c_int(0), C.c_int(0)
+    bpath = os.fsencode(path)
+    check(lib().vsc_flo_read_header(bpath, C.byref(w), C.byref(h)), os.fspath(path))
+    out = pinned_empty((h.value, w.value, 2), torch.float32) if pinned else torch.empty((h.value, w.value, 2))
+    check(lib().vsc_flo_read(bpath, C.c_void_p(out.data_ptr()), C.c_size_t(out.numel()), C.byref(w), C.byref(h)),
+          os.fspath(path))
+    return out

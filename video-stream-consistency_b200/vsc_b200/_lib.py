@@ -48,11 +48,15 @@ PROTOTYPES = {
     "vsc_stabilizer_step": (_i, [_p, _p, _p, _p]),
     "vsc_stabilizer_step_lowres_flow": (_i, [_p, _p, _p, _i, _i, _p]),
     "vsc_stabilizer_step_host_flow": (_i, [_p, _p, _p, _i, _i, _p]),
+    "vsc_stabilizer_step_flow_files": (_i, [_p, C.c_char_p, _i, _p]),
     "vsc_stabilizer_sync": (_i, [_p]),
     "vsc_stabilizer_last_output_dev": (_p, [_p]),
     "vsc_stabilizer_copy_last_output": (_i, [_p, _p]),
     "vsc_stabilizer_compute_stream": (_p, [_p]),
     "vsc_stabilizer_reset": (_i, [_p]),
+    "vsc_flo_read_header": (_i, [C.c_char_p, _p, _p]),
+    "vsc_flo_read": (_i, [C.c_char_p, _p, _sz, _p, _p]),
+    "vsc_flo_frame_path": (_i, [C.c_char_p, _i, _i, C.c_char_p, _sz]),
     "vsc_host_alloc": (_i, [_p, _sz]),
     "vsc_host_free": (_i, [_p]),
 }
@@ -76,7 +80,7 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def check(rc: int) -> None:
+def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().vsc_error_string(int(rc))
-        raise VscError(f"vsc error {rc}: {msg.decode() if msg else '?'}")
+        raise VscError(f"vsc error {rc}: {msg.decode() if msg else '?'}" + (f" {what}" if what else ""))
