@@ -54,6 +54,14 @@ WORKLOADS = {
                           "full stabilization (BASELINE configs[2])"),
     "4k-stab": dict(W=3840, H=2160, flowW=3840, flowH=2160, corr=[], warp=[],
                     desc="precomputed-flow stabilization only at 4K (BASELINE configs[3])"),
+    # file mode of configs[3] (-f <flowdir>): the e2e arm also reads the two .flo files of every frame from disk
+    # (page cache) through vsc_stabilizer_step_flow_files + prefetch of the next frame's pair
+    "4k-stab-files": dict(W=3840, H=2160, flowW=3840, flowH=2160, corr=[], warp=[], files=True,
+                          desc="precomputed-flow stabilization at 4K, flows ingested from .flo files in the e2e arm "
+                               "(BASELINE configs[3], file mode)"),
+    "1080p-stab-files": dict(W=1920, H=1080, flowW=1920, flowH=1080, corr=[], warp=[], files=True,
+                             desc="precomputed-flow stabilization at 1080p, flows ingested from .flo files in the "
+                                  "e2e arm"),
 }
 NFRAMES = 8  # distinct synthetic frame pairs, cycled
 
@@ -208,7 +216,9 @@ def bench_ours(args, rank, world):
     peaks, peak_src = measured_peaks()
 
     ho, hp = make_host_frames(W, H, pin=True)
-    flf, flb = synth.flows(fw, fh, 3)
+    files = bool(wl.get("files"))
+    flow_c = 2 if files else 3    # .flo files hold (u, v) pairs
+    flf, flb = synth.flows(fw, fh, flow_c)
     d_flf, d_flb = torch.from_numpy(flf).to(dev), torch.from_numpy(flb).to(dev)
     sets = make_op_tensors(wl, dev)
     hpar = V.HyperParams()
@@ -244,7 +254,7 @@ def bench_ours(args, rank, world):
             V.check(L.vsc_bilinear(dptr(d_flb), fw, fh, 3, dptr(upb), W, H, 3, stream()))
         i0, i1, i2 = stream_frame_index(t)
         V.frame_stabilize(d_o[i0], d_o[i1], d_o[i2], d_p[i0], d_p[i1], d_p[i2], last, upf, upb, hpar, out=cons,
-                          workspace=ws)
+                          workspace=ws)   # flow channel count is taken from the flow tensors
         V.check(L.vsc_f32x3_to_rgba8(dptr(cons), dptr(out8), W, H, stream()))
         last, cons = cons, last
 
@@ -277,14 +287,31 @@ def bench_ours(args, rank, world):
     ms_res = e0.elapsed_time(e1)
 
     # ---------------- end-to-end arm: host frame buffers through the pipeline object ----------------
-    st = V.Stabilizer(W, H, 3)
+    st = V.Stabilizer(W, H, flow_c)
     outs = [V.pinned_empty((H, W, 4)) for _ in range(2)]
     ext = torch.cuda.ExternalStream(st.compute_stream, device=dev)
+    flow_dir, NFLO = None, 3
+    if files:
+        import shutil
+        import tempfile
+
+        # frames 1..NFLO cycle: forward file of frame i is frame_(i+1).flo, backward file frame_(i)_bwd.flo
+        flow_dir = tempfile.mkdtemp(prefix=f"vsc_flo_r{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        hdr = b"PIEH" + np.array([fw, fh], np.int32).tobytes()
+        for i in range(1, NFLO + 1):
+            for path, arr in ((V.flo_frame_path(flow_dir, i + 1), flf), (V.flo_frame_path(flow_dir, i, True), flb)):
+                with open(path, "wb") as f:
+                    f.write(hdr)
+                    f.write(np.roll(arr, i, axis=1).tobytes())
 
     def step_e2e(t):
-        with torch.cuda.stream(ext):  # custom ops share the pipeline's compute stream
-            run_ops(V, sets)
-        st.step(d_flf, d_flb, outs[t & 1])
+        if files:
+            st.step_flow_files(flow_dir, 1 + t % NFLO, outs[t & 1])
+            st.prefetch_flow_files(flow_dir, 1 + (t + 1) % NFLO)
+        else:
+            with torch.cuda.stream(ext):  # custom ops share the pipeline's compute stream
+                run_ops(V, sets)
+            st.step(d_flf, d_flb, outs[t & 1])
         st.push_frame(ho[(t + 2) % NFRAMES], hp[(t + 2) % NFRAMES])
 
     for t in range(3):
@@ -302,6 +329,8 @@ def bench_ours(args, rank, world):
     ms_e2e = (t1 - t0) * 1e3
     clk = clocks.stop(t_host0, t1)
     st.close()
+    if flow_dir:
+        shutil.rmtree(flow_dir, ignore_errors=True)
 
     # ---------------- roofline of the dominant kernel: the level-0 solver ----------------
     # marginal time of n sweeps = t(2n) - t(n), CUDA events on the launching stream.  In the default mode the
@@ -354,7 +383,9 @@ def bench_ours(args, rank, world):
                        else f"{NFRAMES} frame pairs cycled; solver state {72 * W * H / 1e6:.0f} MB per sweep",
                        "custom_op_bytes_per_step": op_bytes(wl),
                        "out_of_scope": "PWC-Net convolutions (ORT graph): synthetic device-resident activations"},
-            "e2e": {"value": aggregate_fps(world, K, ms_e2e), "unit": "frames/s", "h2d_bytes_per_step": 2 * W * H * 4,
+            "e2e": {"value": aggregate_fps(world, K, ms_e2e), "unit": "frames/s",
+                    "h2d_bytes_per_step": 2 * W * H * 4 + (2 * fw * fh * 8 if files else 0),
+                    "file_bytes_per_step": 2 * (12 + fw * fh * 8) if files else 0,
                     "d2h_bytes_per_step": W * H * 4, "timing": "host clock between full device synchronisations",
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),

@@ -231,6 +231,10 @@ VSC_API int vsc_stabilizer_step_host_flow(vsc_stabilizer* s, const float* flowFw
  * created with flow_channels == 2; files of another size than the frame fail with VSC_E_FLO_DIMS. */
 VSC_API int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame,
     uint8_t* out_rgba_host);
+/* optional: start reading the .flo pair of `currentFrame` on a worker thread into the second set of pinned
+ * landing buffers, so that the next vsc_stabilizer_step_flow_files(s, flow_dir, currentFrame, ...) finds it in
+ * memory (file reading overlaps the previous frame's GPU work).  Read errors surface from that step call. */
+VSC_API int vsc_stabilizer_prefetch_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame);
 VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
 /* device pointer to the fp32 result of the last step (W*H*3 floats), for tests */
 VSC_API const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s);

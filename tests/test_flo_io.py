@@ -118,3 +118,22 @@ def test_flo_frame_paths(V):
     assert V.lib().vsc_flo_frame_path(None, 1, 0, buf, 8) == -1
     for code, text in ((-5, "could not open"), (-10, "too short"), (-11, "too long"), (-12, "does not match")):
         assert text in V.lib().vsc_error_string(code).decode()
+
+
+def test_flo_large_files_take_the_parallel_path(V, O, tmp_path):
+    """payloads >= 8 MB are read by several pread threads and size-checked with fstat: same values and the same
+    too-short / too-long verdicts as the reference's row loop + EOF probe"""
+    W, H = 1024, 1100
+    rng = np.random.default_rng(3)
+    ff = rng.standard_normal((H, W, 2)).astype(np.float32)
+    good, short, long_ = (str(tmp_path / n) for n in ("good.flo", "short.flo", "long.flo"))
+    write_flo(good, ff)
+    write_flo(short, ff, drop=4096 * 3 + 1)
+    write_flo(long_, ff, extra=b"\x01\x02")
+    assert np.array_equal(V.flo_read(good).numpy(), ff)
+    for path, text in ((short, "too short"), (long_, "too long")):
+        with pytest.raises(V.VscError, match=text):
+            V.flo_read(path)
+        if O.ref_cpu_available():
+            rc, _, _, _, msg = ref_read(O, path, W * H * 2)
+            assert rc == 1 and text in msg

@@ -492,9 +492,13 @@ def test_flow_directory_step(V, O, dev, tmp_path):
     _write_flo(V.flo_frame_path(other, 1, backward=True), flows[0][1][:, :W - 2])
     with pytest.raises(V.VscError, match="does not match"):
         st.step_flow_files(other, 1, outs[0])
+    st.prefetch_flow_files(d, 77)         # a prefetch nobody collects is dropped; one for a missing file is harmless
     for t, cur in enumerate((1, 2, 3)):   # the refused calls above left the window intact
+        if t == 1:
+            st.prefetch_flow_files(d, cur)    # announced: the step finds the pair in the second landing set
         st.step_flow_files(d, cur, outs[t])
         if t < 2:
+            st.prefetch_flow_files(d, cur + 1) if t == 1 else None
             st.push_frame(o8[3 + t], p8[3 + t])
     st.sync()
     for t in range(3):

@@ -20,6 +20,8 @@
 
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
 
 namespace {
 
@@ -60,6 +62,17 @@ struct vsc_stabilizer {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     int ws_levels = 0;
+
+    // file mode (-f <flowdir>): two sets of pinned landing buffers (allocated on first use), so that a worker
+    // thread can read the .flo pair of the next frame while this frame's pair is uploaded and consumed
+    float* filePin[2][2] = {};
+    cudaEvent_t file_h2d[2] = {};   // copy stream: H2D out of the set finished
+    bool file_used[2] = {};
+    int file_set = 0;               // set the next read goes to
+    std::thread pf_thread;
+    bool pf_active = false;
+    int pf_set = 0, pf_frame = 0, pf_rc = 0;
+    std::string pf_dir;
 
     uint8_t* out_dev[2] = {};
     uint8_t* out_pin[2] = {};
@@ -273,6 +286,13 @@ extern "C" void vsc_stabilizer_destroy(vsc_stabilizer* s)
     if (s->flow_ready) cudaEventDestroy(s->flow_ready);
     if (s->flow_free) cudaEventDestroy(s->flow_free);
     cudaFree(s->ws);
+    if (s->pf_thread.joinable())
+        s->pf_thread.join();
+    for (int k = 0; k < 2; ++k) {
+        cudaFreeHost(s->filePin[k][0]);
+        cudaFreeHost(s->filePin[k][1]);
+        if (s->file_h2d[k]) cudaEventDestroy(s->file_h2d[k]);
+    }
     if (s->compute) cudaStreamDestroy(s->compute);
     if (s->copy) cudaStreamDestroy(s->copy);
     if (s->d2h) cudaStreamDestroy(s->d2h);
@@ -398,8 +418,91 @@ namespace vsc {
 int flo_read_into(const char* path, float* dst, size_t cap_floats, int* width, int* height);  // flo_io.cu
 }
 
-// FileStabilizer::retrieveOpticalFlow (stabilizefiles.cpp:135-149) + doOneStep: the two .flo files of frame
-// `currentFrame` are read straight into the pinned landing buffers and uploaded on the copy stream.
+namespace {
+
+// FileStabilizer::retrieveOpticalFlow (stabilizefiles.cpp:135-149) for frame `currentFrame`, into landing set k
+int read_flow_pair(vsc_stabilizer* s, const std::string& dir, int currentFrame, int k)
+{
+    char path[2][4096];
+    int rc;
+    // "flow file i describes i-1 -> i; bwd flow file describes i -> i-1" (stabilizefiles.cpp:139-144)
+    if ((rc = vsc_flo_frame_path(dir.c_str(), currentFrame + 1, 0, path[0], sizeof(path[0]))))
+        return rc;
+    if ((rc = vsc_flo_frame_path(dir.c_str(), currentFrame, 1, path[1], sizeof(path[1]))))
+        return rc;
+    int res[2] = {VSC_OK, VSC_OK};
+    auto one = [&](int i) {
+        int w = 0, h = 0;
+        // a file of another size must not be read into the frame-sized buffer: check the header first
+        if ((res[i] = vsc_flo_read_header(path[i], &w, &h)))
+            return;
+        if (w != s->W || h != s->H) {
+            res[i] = VSC_E_FLO_DIMS;          // initializeFlowImage, imagehelpers.cpp:45-49
+            return;
+        }
+        res[i] = vsc::flo_read_into(path[i], s->filePin[k][i], s->P * 2, &w, &h);
+    };
+    std::thread other(one, 1);
+    one(0);
+    other.join();
+    return res[0] ? res[0] : res[1];
+}
+
+int ensure_file_buffers(vsc_stabilizer* s)
+{
+    if (s->filePin[0][0])
+        return VSC_OK;
+    int rc = VSC_OK;
+    for (int k = 0; k < 2 && !rc; ++k) {
+        for (int i = 0; i < 2 && !rc; ++i)
+            rc = cu(cudaHostAlloc(reinterpret_cast<void**>(&s->filePin[k][i]), s->P * 2 * sizeof(float),
+                cudaHostAllocDefault));
+        if (!rc)
+            rc = cu(cudaEventCreateWithFlags(&s->file_h2d[k], cudaEventDisableTiming));
+    }
+    return rc;
+}
+
+// set k is about to be overwritten by the host: its previous upload must have left it
+void wait_file_set(vsc_stabilizer* s, int k)
+{
+    if (s->file_used[k])
+        cudaEventSynchronize(s->file_h2d[k]);
+}
+
+void drop_prefetch(vsc_stabilizer* s)
+{
+    if (s->pf_thread.joinable())
+        s->pf_thread.join();
+    s->pf_active = false;
+}
+
+}  // namespace
+
+extern "C" int vsc_stabilizer_prefetch_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame)
+{
+    if (!s || !flow_dir || s->flowC != 2)
+        return VSC_E_INVALID;
+    int rc = ensure_file_buffers(s);
+    if (rc)
+        return rc;
+    if (s->pf_active && s->pf_frame == currentFrame && s->pf_dir == flow_dir)
+        return VSC_OK;   // already on its way
+    drop_prefetch(s);
+    const int k = s->file_set;
+    wait_file_set(s, k);
+    s->pf_set = k;
+    s->pf_frame = currentFrame;
+    s->pf_dir = flow_dir;
+    s->pf_rc = VSC_OK;
+    s->pf_active = true;
+    s->pf_thread = std::thread([s, k, currentFrame]() { s->pf_rc = read_flow_pair(s, s->pf_dir, currentFrame, k); });
+    return VSC_OK;
+}
+
+// FileStabilizer::retrieveOpticalFlow + doOneStep: the two .flo files of frame `currentFrame` are read straight
+// into pinned landing buffers (by the prefetch worker if vsc_stabilizer_prefetch_flow_files announced the
+// frame, else here) and uploaded on the copy stream.
 extern "C" int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame,
     uint8_t* out_rgba_host)
 {
@@ -407,26 +510,27 @@ extern "C" int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flo
         return VSC_E_INVALID;
     if (s->count != 3)
         return VSC_E_STATE;
-    char path[2][4096];
-    int rc;
-    // "flow file i describes i-1 -> i; bwd flow file describes i -> i-1" (stabilizefiles.cpp:139-144)
-    if ((rc = vsc_flo_frame_path(flow_dir, currentFrame + 1, 0, path[0], sizeof(path[0]))))
+    int rc = ensure_file_buffers(s);
+    if (rc)
         return rc;
-    if ((rc = vsc_flo_frame_path(flow_dir, currentFrame, 1, path[1], sizeof(path[1]))))
-        return rc;
-    if (s->flow_used)
-        cudaEventSynchronize(s->flow_ready);  // previous H2D out of the pinned landing buffers finished
-    for (int i = 0; i < 2; ++i) {
-        int w = 0, h = 0;
-        // a file of another size must not be read into the frame-sized buffer: check the header first
-        if ((rc = vsc_flo_read_header(path[i], &w, &h)))
-            return rc;
-        if (w != s->W || h != s->H)
-            return VSC_E_FLO_DIMS;            // initializeFlowImage, imagehelpers.cpp:45-49
-        if ((rc = vsc::flo_read_into(path[i], s->flowPin[i], s->P * 2, &w, &h)))
-            return rc;
+    int k;
+    if (s->pf_active && s->pf_frame == currentFrame && s->pf_dir == flow_dir) {
+        drop_prefetch(s);   // joins the worker
+        k = s->pf_set;
+        rc = s->pf_rc;
+    } else {
+        drop_prefetch(s);
+        k = s->file_set;
+        wait_file_set(s, k);
+        rc = read_flow_pair(s, flow_dir, currentFrame, k);
     }
-    return vsc_stabilizer_step_host_flow(s, s->flowPin[0], s->flowPin[1], s->W, s->H, out_rgba_host);
+    if (rc)
+        return rc;
+    rc = vsc_stabilizer_step_host_flow(s, s->filePin[k][0], s->filePin[k][1], s->W, s->H, out_rgba_host);
+    cudaEventRecord(s->file_h2d[k], s->copy);
+    s->file_used[k] = true;
+    s->file_set = k ^ 1;
+    return rc;
 }
 
 extern "C" int vsc_stabilizer_sync(vsc_stabilizer* s)
@@ -456,6 +560,7 @@ extern "C" int vsc_stabilizer_reset(vsc_stabilizer* s)
 {
     if (!s)
         return VSC_E_INVALID;
+    drop_prefetch(s);
     const int rc = vsc_stabilizer_sync(s);
     s->head = 0;
     s->count = 0;

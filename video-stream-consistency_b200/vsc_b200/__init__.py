@@ -307,6 +307,10 @@ class Stabilizer:
         check(lib().vsc_stabilizer_step_flow_files(self._h, os.fsencode(flow_dir), int(current_frame), outp),
               os.fspath(flow_dir))
 
+    def prefetch_flow_files(self, flow_dir: str, current_frame: int):
+        """start reading the .flo pair of `current_frame` in the background (see vsc_stabilizer_prefetch_flow_files)"""
+        check(lib().vsc_stabilizer_prefetch_flow_files(self._h, os.fsencode(flow_dir), int(current_frame)))
+
     def sync(self):
         check(lib().vsc_stabilizer_sync(self._h))
 

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "vsc_stabilizer_step_lowres_flow": (_i, [_p, _p, _p, _i, _i, _p]),
     "vsc_stabilizer_step_host_flow": (_i, [_p, _p, _p, _i, _i, _p]),
     "vsc_stabilizer_step_flow_files": (_i, [_p, C.c_char_p, _i, _p]),
+    "vsc_stabilizer_prefetch_flow_files": (_i, [_p, C.c_char_p, _i]),
     "vsc_stabilizer_sync": (_i, [_p]),
     "vsc_stabilizer_last_output_dev": (_p, [_p]),
     "vsc_stabilizer_copy_last_output": (_i, [_p, _p]),
