@@ -42,12 +42,13 @@ for (W, H) in ((3840, 2160), (1920, 1080), (1280, 720), (960, 540), (640, 360)):
     tg = torch.rand((H, W, 3), device=dev, generator=g)
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
     out = pr.clone()
-    row = []
-    for k in range(0, 5):
-        V.check(L.vsc_set_solver_mode(2 | (k << 8)))
-        time_solve(pr, tg, wt, out, T * 4, reps=2)
-        a = time_solve(pr, tg, wt, out, T * 4)
-        b = time_solve(pr, tg, wt, out, T * 20)
-        row.append((NAMES[k], (b - a) / 16 * 1e3))
-    L.vsc_set_solver_mode(0)
-    print(f"{W}x{H} T={T}: " + "  ".join(f"{n} {us:7.2f} us" for n, us in row), flush=True)
+    for flag, kname in ((0, "1 column/thread"),):
+        row = []
+        for k in range(0, 5):
+            V.check(L.vsc_set_solver_mode(2 | flag | (k << 8)))
+            time_solve(pr, tg, wt, out, T * 4, reps=2)
+            a = time_solve(pr, tg, wt, out, T * 4)
+            b = time_solve(pr, tg, wt, out, T * 20)
+            row.append((NAMES[k], (b - a) / 16 * 1e3))
+        L.vsc_set_solver_mode(0)
+        print(f"{W}x{H} T={T} {kname:26s}: " + "  ".join(f"{n} {us:7.2f} us" for n, us in row), flush=True)

@@ -364,13 +364,14 @@ def test_blocked_solver_is_bit_identical_to_unblocked(V, dev, W, H, iters):
         # blocked kernel variants: neighbour-pair barriers + warp-cooperative staging (default), CTA barrier,
         # per-thread staging
         gots = []
-        for mode in (2, 2 | 0x10, 2 | 0x20):
+        modes = (2, 2 | 0x10, 2 | 0x20)
+        for mode in modes:
             assert L.vsc_set_solver_mode(mode) == 0
             gots.append(V.get_consist_out(pr, tg, wt, iters, 0.15, 0.15, pr.clone()))
     finally:
         L.vsc_set_solver_mode(0)
     torch.cuda.synchronize()
-    for mode, got in zip((2, 0x12, 0x22), gots):
+    for mode, got in zip(modes, gots):
         assert torch.equal(got, ref), (hex(mode), float((got - ref).abs().max()))
 
 
