@@ -172,6 +172,7 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
 extern int g_stream_band;
+extern bool g_stream_pdl;
 bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
 // how `iters` sweeps are executed: n8 passes of 8 sweeps, one pass of `tail` in {0,2,4,6} sweeps, `rest` in {0,1}
@@ -269,12 +270,13 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 
 extern "C" int vsc_set_solver_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x7FF || (mode & 0x80) || ((mode >> 8) & 7) > 4)
+    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x7FF || ((mode >> 8) & 7) > 4)
         return VSC_E_INVALID;
     g_solver_mode = mode & 0xF;
     g_stream_pair = (mode & 0x10) == 0;
     g_stream_coop = (mode & 0x20) == 0;
     g_frame_fused = (mode & 0x40) == 0;
+    g_stream_pdl = (mode & 0x80) == 0;
     g_stream_band = (mode >> 8) & 7;
     return VSC_OK;
 }

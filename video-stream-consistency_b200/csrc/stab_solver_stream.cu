@@ -37,6 +37,7 @@ __host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 :
 __host__ __device__ constexpr int stream_halo(int T) { return (3 * T + 3) / 4 * 4; }
 bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
 bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
+bool g_stream_pdl = true;           // programmatic dependent launch: pass n+1's prologue overlaps pass n's tail
 int g_stream_band = 0;              // 0 = cost model; 1..4 force a band candidate (benchmarks, vsc_set_solver_mode)
 
 // BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best.
@@ -63,6 +64,10 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     // ahead (each thread copies and later reads only its own 4 floats per row: no cross-thread ordering needed)
     float* stage = smem_raw + T * 4 * BW + 8;
 
+    // Programmatic dependent launch: let the next pass of the stream start placing its CTAs as ours retire (its
+    // prologue -- index set-up, zeroing of the exchange ring -- then overlaps our tail); it blocks in
+    // griddepcontrol.wait below until this whole grid has completed and flushed, before it touches the images.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
     const int L = 3 * W;
     const int g0 = blockIdx.x * S - HALO;
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous kernel of the stream wrote our inputs
     if constexpr (COOP) {
 #pragma unroll
         for (int j = 0; j < PF - 1; ++j)   // rows of steps 0 .. PF-2
@@ -306,11 +312,20 @@ static int launch_stream_impl(const StreamGeom& g, const float* coefA, const flo
     static unsigned long long configured = 0;
     if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, COOP, PAIR>, smem, false, configured))
         return e;
-    const dim3 grid(g.nb, g.nc);
-    solver_stream_kernel<T, BW, COOP, PAIR><<<grid, BW, smem, st>>>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, g.chunk_rows,
-        step, mom);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.nb, g.nc);
+    cfg.blockDim = dim3(BW);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_stream_pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_stream_kernel<T, BW, COOP, PAIR>, coefA, coefB, u_src, u_dst,
+        o_src, o_dst, W, H, g.chunk_rows, step, mom);
     count_launch();
-    return launch_status();
+    return e == cudaSuccess ? launch_status() : static_cast<int>(e);
 }
 
 template <int T, int BW>
