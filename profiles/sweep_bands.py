@@ -42,7 +42,7 @@ for (W, H) in ((3840, 2160), (1920, 1080), (1280, 720), (960, 540), (640, 360)):
     tg = torch.rand((H, W, 3), device=dev, generator=g)
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
     out = pr.clone()
-    for flag, kname in ((0, "1 column/thread"),):
+    for flag, kname in ((0, "pair barriers"),):
         row = []
         for k in range(0, 5):
             V.check(L.vsc_set_solver_mode(2 | flag | (k << 8)))

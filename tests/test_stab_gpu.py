@@ -364,7 +364,7 @@ def test_blocked_solver_is_bit_identical_to_unblocked(V, dev, W, H, iters):
         # blocked kernel variants: neighbour-pair barriers + warp-cooperative staging (default), CTA barrier,
         # per-thread staging
         gots = []
-        modes = (2, 2 | 0x10, 2 | 0x20)
+        modes = (2, 2 | 0x10, 2 | 0x20, 2 | 0x80)   # ..., without programmatic dependent launch
         for mode in modes:
             assert L.vsc_set_solver_mode(mode) == 0
             gots.append(V.get_consist_out(pr, tg, wt, iters, 0.15, 0.15, pr.clone()))

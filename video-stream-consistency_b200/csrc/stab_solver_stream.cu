@@ -45,8 +45,11 @@ int g_stream_band = 0;              // 0 = cost model; 1..4 force a band candida
 // 4K -- profiles/r1_sweep_bands.txt -- and are not built)
 // COOP: level-0 rows staged warp-cooperatively with 16-byte cp.async (one chunk per lane and row; needs
 // 3W % 4 == 0 and 16-byte aligned images); otherwise every thread stages its own four floats (4-byte cp.async).
-// PAIR: the exchange ring is synchronised between neighbouring warps only (named barriers).
-template <int T, int BW, bool COOP, bool PAIR>
+// SYNC: how the exchange ring is synchronised: 0 = CTA-wide barrier, 1 = between neighbouring warps only (named
+// barriers).  A third scheme -- per-warp progress counters polled with ld.acquire, so that nobody waits for a warp
+// that is behind -- was measured 35 % SLOWER (253 vs 186 us at 4K, profiles/r1_sweep_bands_flags_vs_barriers.txt):
+// the per-step poll sits on every warp's critical path, the named barriers are nearly free.
+template <int T, int BW, bool COOP, int SYNC>
 __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, float step, float mom)
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     constexpr int NW = BW / 32;
     const int warp = tid >> 5;
     auto ring_sync = [&]() {
-        if constexpr (PAIR && NW <= 16) {
+        if constexpr (SYNC == 1 && NW <= 16) {
             const int first = (warp & 1) ? warp + 1 : warp;   // boundary ids: left = warp, right = warp + 1
             const int second = (warp & 1) ? warp : warp + 1;
             if (first >= 1 && first <= NW - 1)
@@ -186,7 +189,6 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             __syncthreads();
         }
     };
-
     // One step of the pipeline.  ROWMASK selects the variant that applies the reference's top/bottom inclusion
     // tests (flowconsistency.cu:227,232); it is needed only while some level works on rows <= 0 or >= H-2, a
     // CTA-uniform condition true for a handful of steps of the first and last row chunk.
@@ -299,18 +301,21 @@ static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
     g.chunk_rows = (H + nc - 1) / nc;
     g.nc = (H + g.chunk_rows - 1) / g.chunk_rows;
     const long long waves = (static_cast<long long>(g.nb) * g.nc + sms - 1) / sms;
-    g.cost = waves * (g.chunk_rows + 3 * T) * BW;
+    // measured time of one step in ns (profiles/r1_sweep_bands*.txt, T = 8, 640x360 ... 4K): not proportional to the
+    // band width -- a narrow band has fewer warps to hide its per-step latency
+    const int step_ns = BW >= 512 ? 450 : BW >= 448 ? 405 : BW >= 384 ? 325 : 258;
+    g.cost = waves * (g.chunk_rows + 3 * T) * step_ns;
     return g;
 }
 
-template <int T, int BW, bool COOP, bool PAIR>
+template <int T, int BW, bool COOP, int SYNC>
 static int launch_stream_impl(const StreamGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     constexpr int PF = COOP ? 2 * T : stream_private_pf(T);
     const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static unsigned long long configured = 0;
-    if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, COOP, PAIR>, smem, false, configured))
+    if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, COOP, SYNC>, smem, false, configured))
         return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.nb, g.nc);
@@ -322,7 +327,7 @@ static int launch_stream_impl(const StreamGeom& g, const float* coefA, const flo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_stream_pdl ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_stream_kernel<T, BW, COOP, PAIR>, coefA, coefB, u_src, u_dst,
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_stream_kernel<T, BW, COOP, SYNC>, coefA, coefB, u_src, u_dst,
         o_src, o_dst, W, H, g.chunk_rows, step, mom);
     count_launch();
     return e == cudaSuccess ? launch_status() : static_cast<int>(e);
@@ -335,11 +340,10 @@ static int launch_stream(const StreamGeom& g, const float* coefA, const float* c
     const bool coop = (3LL * W) % 4 == 0 && aligned16(coefA) && aligned16(coefB) && aligned16(u_src) && aligned16(o_src)
         && g_stream_coop;
     if (coop && g_stream_pair)
-        return launch_stream_impl<T, BW, true, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        return launch_stream_impl<T, BW, true, 1>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (coop)
-        return launch_stream_impl<T, BW, true, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom,
-            st);
-    return launch_stream_impl<T, BW, false, false>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+        return launch_stream_impl<T, BW, true, 0>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    return launch_stream_impl<T, BW, false, 0>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
 }
 
 template <int T>
