@@ -304,7 +304,17 @@ def bench_ours(args, rank, world):
                     f.write(hdr)
                     f.write(np.roll(arr, i, axis=1).tobytes())
 
+    # flow network input (FlowModel::run's frame path, on the device): the three window frames at the network's
+    # input size (frame size / FLOWDOWNSCALE rounded up to a multiple of 64, convert_onnx.py:17-20)
+    net = None
+    if wl["corr"]:
+        net = ((fw + 63) // 64 * 64, (fh + 63) // 64 * 64)
+        net_in = [torch.empty((net[1], net[0], 4), device=dev, dtype=torch.uint8) for _ in range(3)]
+
     def step_e2e(t):
+        if net:
+            for i in range(3):
+                st.flow_input(i, net[0], net[1], net_in[i])
         if files:
             st.step_flow_files(flow_dir, 1 + t % NFLO, outs[t & 1])
             st.prefetch_flow_files(flow_dir, 1 + (t + 1) % NFLO)

@@ -148,6 +148,13 @@ VSC_API int vsc_set_solver_mode(int mode);
 VSC_API int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, int H, vsc_stream_t stream);
 VSC_API int vsc_f32x3_to_rgba8(const float* in, uint8_t* rgba_dev, int W, int H, vsc_stream_t stream);
 
+/* Nearest-neighbour scaling of an RGBA8888 device image, sampled at pixel centres in 16.16 fixed point
+ * (source x = (ix / 2 + x * ix) >> 16, ix = 65536 * srcW / dstW truncated; same in y): the device-side
+ * replacement for the CPU QImage::scaled(..., Qt::FastTransformation) in FlowModel::run (flowmodel.cpp:126-131),
+ * so that the flow network's input is produced from the frame already resident on the GPU. */
+VSC_API int vsc_rgba8_scale_nearest(const uint8_t* src_dev, int srcW, int srcH, uint8_t* dst_dev, int dstW, int dstH,
+    vsc_stream_t stream);
+
 /* Fused "stage A" of doOneStep (videostabilizer.cpp:182-198): the five get_warp_result calls,
  * get_adap_comb and get_consist_wt in ONE pass -- no warped intermediates touch HBM.
  * Outputs adapCmbPr and consWt (and adapCmbIn if non-NULL). */
@@ -236,6 +243,11 @@ VSC_API int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flow_d
  * landing buffers, so that the next vsc_stabilizer_step_flow_files(s, flow_dir, currentFrame, ...) finds it in
  * memory (file reading overlaps the previous frame's GPU work).  Read errors surface from that step call. */
 VSC_API int vsc_stabilizer_prefetch_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame);
+/* FlowModel::run input path without the host (flowmodel.cpp:121-150): writes window frame `window_index`
+ * (0 = previous, 1 = current, 2 = next; the ORIGINAL stream) as RGBA8888 at netW x netH into dst_dev -- e.g. the
+ * flow session's bound input tensor -- scaling with vsc_rgba8_scale_nearest when the size differs.  Enqueued on
+ * the compute stream; requires 3 frames in the window. */
+VSC_API int vsc_stabilizer_flow_input(vsc_stabilizer* s, int window_index, uint8_t* dst_dev, int netW, int netH);
 VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
 /* device pointer to the fp32 result of the last step (W*H*3 floats), for tests */
 VSC_API const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s);

@@ -511,3 +511,56 @@ def test_flow_directory_step(V, O, dev, tmp_path):
     with pytest.raises(V.VscError):
         st3.step_flow_files(d, 1)
     st3.close()
+
+
+def _scale_nearest_np(img, dw, dh):
+    """the definition in include/vsc/vsc.h: 16.16 fixed point, pixel-centre sampling"""
+    sh, sw, _ = img.shape
+    ix = int(65536.0 * sw / dw)
+    iy = int(65536.0 * sh / dh)
+    xs = np.minimum((ix // 2 + np.arange(dw, dtype=np.int64) * ix) >> 16, sw - 1)
+    ys = np.minimum((iy // 2 + np.arange(dh, dtype=np.int64) * iy) >> 16, sh - 1)
+    return img[ys][:, xs]
+
+
+@pytest.mark.parametrize("src,dst", [((64, 48), (32, 24)), ((1920, 1080), (960, 576)), ((45, 37), (64, 64)),
+                                     ((100, 7), (33, 5)), ((8, 8), (8, 8)), ((3840, 2160), (3840, 2176))])
+def test_rgba8_scale_nearest(V, dev, src, dst):
+    """device-side flow-network input scaling (SURVEY 8(f)1): the documented fixed-point definition, byte for byte;
+    a factor-2 reduction picks the odd pixels (centre sampling)"""
+    (sw, sh), (dw, dh) = src, dst
+    rng = np.random.default_rng(sw * 7 + dh)
+    img = rng.integers(0, 256, (sh, sw, 4), dtype=np.uint8)
+    got = V.rgba8_scale_nearest(cu(img, dev), dw, dh).cpu().numpy()
+    assert np.array_equal(got, _scale_nearest_np(img, dw, dh))
+    if (sw, sh) == (2 * dw, 2 * dh):
+        assert np.array_equal(got, img[1::2, 1::2])
+    if src == dst:
+        assert np.array_equal(got, img)
+    assert V.lib().vsc_rgba8_scale_nearest(None, 1, 1, None, 1, 1, None) == -1
+
+
+def test_stabilizer_flow_input(V, dev):
+    """the flow network's input frames come from the window already resident on the GPU"""
+    W, H = 64, 48
+    o8, p8 = synth.frames(W, H, 4, seed=97)
+    st = V.Stabilizer(W, H, 3)
+    with pytest.raises(V.VscError):
+        st.flow_input(0, 32, 24)            # window not filled yet
+    for t in range(3):
+        st.push_frame(o8[t], p8[t])
+    for idx in range(3):
+        full = st.flow_input(idx, W, H)
+        half = st.flow_input(idx, 32, 24)
+        st.sync()
+        assert np.array_equal(full.cpu().numpy(), o8[idx])
+        assert np.array_equal(half.cpu().numpy(), _scale_nearest_np(o8[idx], 32, 24))
+    ff, fb = synth.flows(W, H, 3)
+    st.step(cu(ff, dev), cu(fb, dev))
+    st.push_frame(o8[3], p8[3])
+    cur = st.flow_input(1, W, H)            # the window moved on by one frame
+    st.sync()
+    assert np.array_equal(cur.cpu().numpy(), o8[2])
+    with pytest.raises(V.VscError):
+        st.flow_input(3, W, H)
+    st.close()

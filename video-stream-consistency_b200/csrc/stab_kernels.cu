@@ -207,6 +207,46 @@ extern "C" int vsc_bilinear(const float* in, int Wi, int Hi, int Ci, float* out,
     return launch_status();
 }
 
+// Device-side input path for the flow network.  FlowModel::run scales the three window frames on
+// the CPU with QImage::scaled(w, h, Qt::IgnoreAspectRatio, Qt::FastTransformation) and copies them through two
+// host buffers and a pageable H2D per direction (flowmodel.cpp:121-150, imagehelpers.cpp:22-40).  Here the RGBA8
+// frame already uploaded for the stabilization is scaled on the device: nearest neighbour, sampled at pixel
+// centres in 16.16 fixed point (ix = 65536 * sw / dw truncated, source x = (ix / 2 + x * ix) >> 16) -- the scheme
+// of Qt 5's raster scaler as far as it is documented; Qt is not in this image, so byte-equality with
+// QImage::scaled is NOT claimed or tested (the definition above is, tests/test_ops_gpu.py).
+namespace vsc {
+__global__ void __launch_bounds__(256) rgba8_scale_nearest_kernel(const uchar4* __restrict__ src, int sw, int sh,
+    uchar4* __restrict__ dst, int dw, int dh, unsigned ix, unsigned iy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= dw)
+        return;
+    const unsigned sx = min((ix / 2 + static_cast<unsigned>(x) * ix) >> 16, static_cast<unsigned>(sw - 1));
+    const unsigned sy = min((iy / 2 + static_cast<unsigned>(y) * iy) >> 16, static_cast<unsigned>(sh - 1));
+    dst[static_cast<size_t>(y) * dw + x] = __ldg(src + static_cast<size_t>(sy) * sw + sx);
+}
+}  // namespace vsc
+
+extern "C" int vsc_rgba8_scale_nearest(const uint8_t* src_dev, int srcW, int srcH, uint8_t* dst_dev, int dstW, int dstH,
+    vsc_stream_t stream)
+{
+    using namespace vsc;
+    if (!src_dev || !dst_dev || srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0 || dstH > 65535 || srcW > 32767
+        || srcH > 32767 || dstW > 32767)
+        return VSC_E_INVALID;
+    if (!aligned4(src_dev) || !aligned4(dst_dev))
+        return VSC_E_ALIGN;
+    const unsigned ix = static_cast<unsigned>(65536.0 * static_cast<double>(srcW) / static_cast<double>(dstW));
+    const unsigned iy = static_cast<unsigned>(65536.0 * static_cast<double>(srcH) / static_cast<double>(dstH));
+    // (ix / 2 + x * ix) must fit 32 bits: x * ix < dstW * 65536 * srcW / dstW = 65536 * srcW <= 2^31
+    const dim3 grid(cdiv(dstW, 256), dstH);
+    rgba8_scale_nearest_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uchar4*>(src_dev), srcW, srcH,
+        reinterpret_cast<uchar4*>(dst_dev), dstW, dstH, ix, iy);
+    count_launch();
+    return launch_status();
+}
+
 extern "C" int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, int H, vsc_stream_t stream)
 {
     if (!rgba_dev || !out || W <= 0 || H <= 0)

@@ -533,6 +533,23 @@ extern "C" int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flo
     return rc;
 }
 
+extern "C" int vsc_stabilizer_flow_input(vsc_stabilizer* s, int window_index, uint8_t* dst_dev, int netW, int netH)
+{
+    if (!s || !dst_dev || window_index < 0 || window_index > 2 || netW <= 0 || netH <= 0)
+        return VSC_E_INVALID;
+    if (s->count != 3)
+        return VSC_E_STATE;
+    const int k = (s->head + window_index) % kSlots;
+    int rc = cu(cudaStreamWaitEvent(s->compute, s->slot_ready[k], 0));
+    if (rc)
+        return rc;
+    // stage_dev[k][0] keeps the slot's original RGBA8 frame until the slot is pushed again, which waits for the
+    // step that releases it -- and that step is enqueued after this call on the same stream
+    if (netW == s->W && netH == s->H)
+        return cu(cudaMemcpyAsync(dst_dev, s->stage_dev[k][0], s->P * 4, cudaMemcpyDeviceToDevice, s->compute));
+    return vsc_rgba8_scale_nearest(s->stage_dev[k][0], s->W, s->H, dst_dev, netW, netH, s->compute);
+}
+
 extern "C" int vsc_stabilizer_sync(vsc_stabilizer* s)
 {
     if (!s)

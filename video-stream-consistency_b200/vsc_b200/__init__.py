@@ -160,6 +160,16 @@ def gpu_to_image(img: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rgba8_scale_nearest(rgba: torch.Tensor, dstW: int, dstH: int) -> torch.Tensor:
+    """RGBA8888 device bytes [H,W,4] -> [dstH,dstW,4], nearest neighbour at pixel centres (vsc_rgba8_scale_nearest)."""
+    H, W, c = (int(v) for v in rgba.shape)
+    if c != 4:
+        raise VscError("rgba8_scale_nearest: expected [H,W,4] uint8")
+    out = torch.empty((int(dstH), int(dstW), 4), device=rgba.device, dtype=torch.uint8)
+    check(lib().vsc_rgba8_scale_nearest(_u8(rgba, "rgba"), W, H, _u8(out, "out"), int(dstW), int(dstH), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------ fused per-frame pieces
 class HyperParams(C.Structure):
     """hyperParams (videostabilizer.h:38-46), same field order; defaults of initHyperParams."""
@@ -306,6 +316,15 @@ class Stabilizer:
         outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
         check(lib().vsc_stabilizer_step_flow_files(self._h, os.fsencode(flow_dir), int(current_frame), outp),
               os.fspath(flow_dir))
+
+    def flow_input(self, window_index: int, netW: int, netH: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """RGBA8 frame `window_index` (0 prev, 1 cur, 2 next) of the original stream at the flow network's input
+        size, produced on the device (FlowModel::run's input path); ordered on the pipeline's compute stream."""
+        if out is None:
+            out = torch.empty((int(netH), int(netW), 4), device=torch.device("cuda", torch.cuda.current_device()),
+                              dtype=torch.uint8)
+        check(lib().vsc_stabilizer_flow_input(self._h, int(window_index), _u8(out, "out"), int(netW), int(netH)))
+        return out
 
     def prefetch_flow_files(self, flow_dir: str, current_frame: int):
         """start reading the .flo pair of `current_frame` in the background (see vsc_stabilizer_prefetch_flow_files)"""

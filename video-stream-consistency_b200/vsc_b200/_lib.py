@@ -35,6 +35,7 @@ PROTOTYPES = {
     "vsc_set_warp_mode": (_i, [_i]),
     "vsc_rgba8_to_f32x3": (_i, [_p, _p, _i, _i, _p]),
     "vsc_f32x3_to_rgba8": (_i, [_p, _p, _i, _i, _p]),
+    "vsc_rgba8_scale_nearest": (_i, [_p, _i, _i, _p, _i, _i, _p]),
     "vsc_stage_a_fused": (_i, [_p] * 9 + [_i, _f, _f, _f, _p, _p, _p, _i, _i, _p]),
     "vsc_hyper_params_default": (None, [_p]),
     "vsc_frame_solve_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -50,6 +51,7 @@ PROTOTYPES = {
     "vsc_stabilizer_step_host_flow": (_i, [_p, _p, _p, _i, _i, _p]),
     "vsc_stabilizer_step_flow_files": (_i, [_p, C.c_char_p, _i, _p]),
     "vsc_stabilizer_prefetch_flow_files": (_i, [_p, C.c_char_p, _i]),
+    "vsc_stabilizer_flow_input": (_i, [_p, _i, _p, _i, _i]),
     "vsc_stabilizer_sync": (_i, [_p]),
     "vsc_stabilizer_last_output_dev": (_p, [_p]),
     "vsc_stabilizer_copy_last_output": (_i, [_p, _p]),
