@@ -46,7 +46,10 @@ def test_warp_result_exact(V, O, dev, W, H, fc):
 
 @pytest.mark.parametrize("Wi,Hi,Wo,Ho,C", [(64, 48, 32, 24, 3), (45, 37, 22, 18, 3), (22, 18, 45, 37, 3),
                                             (960, 540, 1920, 1080, 3), (31, 17, 64, 40, 2), (5, 5, 5, 5, 3),
-                                            (7, 3, 1, 1, 3)])
+                                            (7, 3, 1, 1, 3),
+                                            # exact x2 up-scales: the value-per-thread kernel (2- and 3-channel)
+                                            (31, 17, 62, 34, 2), (45, 37, 90, 74, 3), (1, 1, 2, 2, 3),
+                                            (1920, 1080, 3840, 2160, 3), (960, 540, 1920, 1080, 2)])
 def test_bilinear_exact(V, O, dev, Wi, Hi, Wo, Ho, C):
     rng = np.random.default_rng(Wi * 7 + Ho)
     img = rng.random((Hi, Wi, C), dtype=np.float32)

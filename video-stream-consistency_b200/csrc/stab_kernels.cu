@@ -109,6 +109,38 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__
     }
 }
 
+// The exact x2 up-scale (flow 960x540 -> 1080p, pyramid level 1 -> 0: the only up-scales of the pipeline), one
+// thread per INPUT value, which owns the 2x2 output values that sample around it.  With Wo = 2 Wi and
+// ox * Wi < 2^24 the reference's coordinate (float(ox) * float(Wi)) / float(Wo) is exactly ox / 2 (exact product,
+// exactly representable quotient), so ix = ox >> 1 and fx is 0 or 0.5 without a division; the four taps are loaded
+// once for four outputs, and the interpolation expression is the reference's, evaluated in its order for each
+// output: bit-identical to bilinear_kernel at a quarter of its loads and none of its divisions.
+template <int C>
+__global__ void __launch_bounds__(256) bilinear_up2_kernel(const float* __restrict__ in, int Wi, int Hi,
+    float* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float index inside the input row
+    const int iy = blockIdx.y;
+    if (i >= Wi * C)
+        return;
+    const int ix = i / C;
+    const int c = i - ix * C;
+    const int dx = (ix + 1 < Wi) ? C : 0;                  // min(ix + 1, Wi - 1)
+    const float* r0 = in + static_cast<size_t>(iy) * Wi * C + i;
+    const float* r1 = (iy + 1 < Hi) ? r0 + static_cast<size_t>(Wi) * C : r0;
+    const float v00 = __ldg(r0), v10 = __ldg(r0 + dx), v01 = __ldg(r1), v11 = __ldg(r1 + dx);
+    auto interp = [&](float fx, float fy) {
+        const float ofx = 1.0f - fx, ofy = 1.0f - fy;
+        return v00 * ofx * ofy + v10 * fx * ofy + v01 * ofx * fy + v11 * fx * fy;
+    };
+    const size_t Lo = static_cast<size_t>(Wi) * 2 * C;
+    float* o = out + static_cast<size_t>(2 * iy) * Lo + static_cast<size_t>(2 * ix) * C + c;
+    __stcs(o, interp(0.0f, 0.0f));
+    __stcs(o + C, interp(0.5f, 0.0f));
+    __stcs(o + Lo, interp(0.0f, 0.5f));
+    __stcs(o + Lo + C, interp(0.5f, 0.5f));
+}
+
 // kernel_to_float_image, gpuimage.cu:39-51.  float(double(u8)/255.0) == float(u8)/255.0f for all 256 inputs
 // (checked exhaustively in tests/test_oracle.py), so the IEEE float division is used.
 __global__ void __launch_bounds__(256) rgba8_to_f32x3_kernel(const uchar4* __restrict__ in, float* __restrict__ out,
@@ -201,6 +233,16 @@ extern "C" int vsc_bilinear(const float* in, int Wi, int Hi, int Ci, float* out,
 {
     if (!in || !out || Wi <= 0 || Hi <= 0 || Ci <= 0 || Wo <= 0 || Ho <= 0 || Co <= 0 || Co > Ci || Ho > 65535)
         return VSC_E_INVALID;
+    if (Wo == 2 * Wi && Ho == 2 * Hi && Ci == Co && (Co == 3 || Co == 2) && static_cast<long long>(Wo) * Wi <= (1 << 24)
+        && static_cast<long long>(Ho) * Hi <= (1 << 24) && static_cast<long long>(Wi) * Ci < (1 << 29)) {
+        const dim3 grid2(cdiv(static_cast<long long>(Wi) * Co, 256), Hi);
+        if (Co == 3)
+            bilinear_up2_kernel<3><<<grid2, 256, 0, as_stream(stream)>>>(in, Wi, Hi, out);
+        else
+            bilinear_up2_kernel<2><<<grid2, 256, 0, as_stream(stream)>>>(in, Wi, Hi, out);
+        count_launch();
+        return launch_status();
+    }
     const dim3 grid(cdiv(Wo, 256), Ho);
     bilinear_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, Wi, Hi, Ci, out, Wo, Ho, Co);
     count_launch();
@@ -213,7 +255,7 @@ extern "C" int vsc_bilinear(const float* in, int Wi, int Hi, int Ci, float* out,
 // frame already uploaded for the stabilization is scaled on the device: nearest neighbour, sampled at pixel
 // centres in 16.16 fixed point (ix = 65536 * sw / dw truncated, source x = (ix / 2 + x * ix) >> 16) -- the scheme
 // of Qt 5's raster scaler as far as it is documented; Qt is not in this image, so byte-equality with
-// QImage::scaled is NOT claimed or tested (the definition above is, tests/test_ops_gpu.py).
+// QImage::scaled is NOT claimed or tested (the definition above is, tests/test_stab_gpu.py).
 namespace vsc {
 __global__ void __launch_bounds__(256) rgba8_scale_nearest_kernel(const uchar4* __restrict__ src, int sw, int sh,
     uchar4* __restrict__ dst, int dw, int dh, unsigned ix, unsigned iy)
