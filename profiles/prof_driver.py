@@ -32,6 +32,13 @@ for (W, H) in ((3840, 2160), (1920, 1080)):
         out = pr.clone()
         V.get_consist_out(pr, tg, wt, 16, 0.15, 0.15, out)
         torch.cuda.synchronize()
+    if "solver10" in which:   # the 10-sweep pass used on large images
+        pr, tg, wt = rnd(H, W, 3), rnd(H, W, 3), rnd(H, W, 3) * 2
+        out = pr.clone()
+        V.check(V.lib().vsc_set_solver_mode(0x2002))
+        V.get_consist_out(pr, tg, wt, 20, 0.15, 0.15, out)
+        V.lib().vsc_set_solver_mode(0)
+        torch.cuda.synchronize()
     if "stage_a" in which:
         ims = [rnd(H, W, 3) for _ in range(7)]
         ff, fb = (torch.from_numpy(x).to(dev) for x in synth.flows(W, H, 3))  # smooth, like real optical flow

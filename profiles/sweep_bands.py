@@ -42,13 +42,16 @@ for (W, H) in ((3840, 2160), (1920, 1080), (1280, 720), (960, 540), (640, 360)):
     tg = torch.rand((H, W, 3), device=dev, generator=g)
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
     out = pr.clone()
-    for flag, kname in ((0, "pair barriers"),):
+    for tmain in (8, 10):
         row = []
         for k in range(0, 5):
-            V.check(L.vsc_set_solver_mode(2 | flag | (k << 8)))
-            time_solve(pr, tg, wt, out, T * 4, reps=2)
-            a = time_solve(pr, tg, wt, out, T * 4)
-            b = time_solve(pr, tg, wt, out, T * 20)
+            if tmain > 8 and k in (1, 2):
+                continue
+            V.check(L.vsc_set_solver_mode(2 | (k << 8) | (((tmain - 6) // 2) << 12)))
+            time_solve(pr, tg, wt, out, tmain * 4, reps=2)
+            a = time_solve(pr, tg, wt, out, tmain * 4)
+            b = time_solve(pr, tg, wt, out, tmain * 20)
             row.append((NAMES[k], (b - a) / 16 * 1e3))
         L.vsc_set_solver_mode(0)
-        print(f"{W}x{H} T={T} {kname:26s}: " + "  ".join(f"{n} {us:7.2f} us" for n, us in row), flush=True)
+        print(f"{W}x{H} T={tmain:2d}: " + "  ".join(f"{n} {us:7.2f} us/pass {us / tmain:6.2f} us/sweep" for n, us in row),
+              flush=True)

@@ -351,7 +351,7 @@ def test_sequence_vs_reference_gpu_fixtures(V, dev, tag, pname):
 # ---------------------------------------------------------------- temporally blocked solver passes
 @pytest.mark.parametrize("W,H", [(400, 300), (64, 48), (45, 37), (157, 101), (1000, 64), (16, 200), (1280, 720),
                                  (1920, 1080), (3840, 2160), (960, 540)])
-@pytest.mark.parametrize("iters", [2, 4, 6, 7, 8, 9, 12, 14, 75, 150])
+@pytest.mark.parametrize("iters", [2, 4, 6, 7, 8, 9, 12, 14, 21, 75, 150])
 def test_blocked_solver_is_bit_identical_to_unblocked(V, dev, W, H, iters):
     """The streaming kernel (8 / 4 sweeps per launch, intermediate sweeps on chip) must reproduce the plain
     Jacobi sweeps bit for bit: same arithmetic per value, only the schedule differs."""
@@ -367,7 +367,9 @@ def test_blocked_solver_is_bit_identical_to_unblocked(V, dev, W, H, iters):
         # blocked kernel variants: neighbour-pair barriers + warp-cooperative staging (default), CTA barrier,
         # per-thread staging
         gots = []
-        modes = (2, 2 | 0x10, 2 | 0x20, 2 | 0x80)   # ..., without programmatic dependent launch
+        # ..., without programmatic dependent launch, main passes forced to 8 / 10 sweeps (the latter also with
+        # per-thread staging)
+        modes = (2, 2 | 0x10, 2 | 0x20, 2 | 0x80, 2 | 0x1000, 2 | 0x2000, 2 | 0x2020)
         for mode in modes:
             assert L.vsc_set_solver_mode(mode) == 0
             gots.append(V.get_consist_out(pr, tg, wt, iters, 0.15, 0.15, pr.clone()))

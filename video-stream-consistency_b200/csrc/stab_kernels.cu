@@ -143,16 +143,17 @@ __global__ void __launch_bounds__(256) bilinear_up2_kernel(const float* __restri
 
 // kernel_to_float_image, gpuimage.cu:39-51.  float(double(u8)/255.0) == float(u8)/255.0f for all 256 inputs
 // (checked exhaustively in tests/test_oracle.py), so the IEEE float division is used.
-__global__ void __launch_bounds__(256) rgba8_to_f32x3_kernel(const uchar4* __restrict__ in, float* __restrict__ out,
-    size_t P)
+// One thread per output VALUE: the stores are contiguous 128-byte lines (a thread per pixel writes three floats at
+// a 12-byte stride: 3x the store sectors, 13.8 us at 1080p against 5 us of compulsory traffic).
+__global__ void __launch_bounds__(256) rgba8_to_f32x3_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
+    size_t n3)
 {
-    const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p >= P)
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n3)
         return;
-    const uchar4 v = in[p];
-    out[p * 3 + 0] = static_cast<float>(v.x) / 255.0f;
-    out[p * 3 + 1] = static_cast<float>(v.y) / 255.0f;
-    out[p * 3 + 2] = static_cast<float>(v.z) / 255.0f;
+    const size_t p = i / 3;
+    const unsigned c = static_cast<unsigned>(i - p * 3);
+    __stcs(out + i, static_cast<float>(__ldg(in + p * 4 + c)) / 255.0f);
 }
 
 // kernel_to_char_image, gpuimage.cu:54-67: floor(|v|*255) to uint32 (saturating, NaN->0), low 8 bits, alpha = 1
@@ -296,8 +297,7 @@ extern "C" int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, in
     if (!aligned4(rgba_dev))
         return VSC_E_ALIGN;
     const size_t P = static_cast<size_t>(W) * H;
-    rgba8_to_f32x3_kernel<<<cdiv(P, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uchar4*>(rgba_dev), out,
-        P);
+    rgba8_to_f32x3_kernel<<<cdiv(static_cast<long long>(P) * 3, 256), 256, 0, as_stream(stream)>>>(rgba_dev, out, P * 3);
     count_launch();
     return launch_status();
 }

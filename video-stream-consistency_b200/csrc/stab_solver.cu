@@ -175,22 +175,30 @@ extern int g_stream_band;
 extern bool g_stream_pdl;
 bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
-// how `iters` sweeps are executed: n8 passes of 8 sweeps, one pass of `tail` in {0,2,4,6} sweeps, `rest` in {0,1}
-// single unblocked sweeps (150 = 18x8 + 6, 75 = 9x8 + 2 + 1)
+int g_stream_tmain = 0;                     // sweeps per main blocked pass: 0 = chosen per solve, else 8 or 10
+
+// how `iters` sweeps are executed: n8 passes of `tmain` sweeps, one pass of `tail` (even, < tmain) sweeps, `rest`
+// in {0,1} single unblocked sweeps (tmain = 8: 150 = 18x8 + 6, 75 = 9x8 + 2 + 1)
 struct SweepPlan {
-    int n8, tail, rest;
+    int n8, tail, rest, tmain;
     int flips() const { return n8 + (tail ? 1 : 0) + rest; }  // number of out-buffer ping-pongs
 };
 
 static SweepPlan plan_sweeps(int W, int H, int iters)
 {
-    SweepPlan p{0, 0, iters};
+    SweepPlan p{0, 0, iters, 8};
     // tiny images: the 3T-step pipeline fill and the 6T-float band halo dominate -> plain sweeps
     const bool big = H >= 48 && 3 * W >= 384;
     if (g_solver_mode == 1 || (g_solver_mode == 0 && !big))
         return p;  // {0, 0, iters}
-    p.n8 = iters / 8;
-    p.tail = (iters % 8) & ~1;
+    // 10-sweep passes pay off on large images only (a pass costs 1.21x an 8-sweep pass at >= 1080p, more below),
+    // and only if they save enough passes: 150 = 15 x 10 against 18 x 8 + 6
+    auto passes = [&](int t) { return iters / t + (((iters % t) & ~1) ? 1 : 0); };
+    const bool large = static_cast<long long>(W) * H >= 1500000;
+    if (g_stream_tmain == 10 || (g_stream_tmain == 0 && large && passes(10) * 121 < passes(8) * 100))
+        p.tmain = 10;
+    p.n8 = iters / p.tmain;
+    p.tail = (iters % p.tmain) & ~1;
     p.rest = iters & 1;
     return p;
 }
@@ -208,7 +216,7 @@ static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, i
     int rc = VSC_OK;
     const int npass = plan.n8 + (plan.tail ? 1 : 0);
     for (int k = 0; k < npass && rc == VSC_OK; ++k) {
-        rc = solver_stream_pass(k < plan.n8 ? 8 : plan.tail, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
+        rc = solver_stream_pass(k < plan.n8 ? plan.tmain : plan.tail, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
         float* t = src; src = dst; dst = t;
         t = us; us = ud; ud = t;
     }
@@ -270,13 +278,14 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 
 extern "C" int vsc_set_solver_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x7FF || ((mode >> 8) & 7) > 4)
+    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x37FF || (mode & 0x800) || ((mode >> 8) & 7) > 4 || ((mode >> 12) & 3) > 2)
         return VSC_E_INVALID;
     g_solver_mode = mode & 0xF;
     g_stream_pair = (mode & 0x10) == 0;
     g_stream_coop = (mode & 0x20) == 0;
     g_frame_fused = (mode & 0x40) == 0;
     g_stream_pdl = (mode & 0x80) == 0;
+    g_stream_tmain = ((mode >> 12) & 3) == 0 ? 0 : 6 + 2 * ((mode >> 12) & 3);
     g_stream_band = (mode >> 8) & 7;
     return VSC_OK;
 }

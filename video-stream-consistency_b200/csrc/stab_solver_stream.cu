@@ -33,7 +33,7 @@
 namespace vsc {
 
 // private staging depth: divides the unroll factor 2T (T in {2, 4, 6, 8})
-__host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 : (T == 2 ? 4 : 8); }
+__host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 : (T == 2 ? 4 : (T == 10 ? 10 : 8)); }
 __host__ __device__ constexpr int stream_halo(int T) { return (3 * T + 3) / 4 * 4; }
 bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
 bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
@@ -375,10 +375,44 @@ static int launch_stream_best(const float* coefA, const float* coefB, const floa
     }
 }
 
-// T in {8, 4}; returns VSC_E_INVALID for any other value (callers fall back to unblocked sweeps)
+// Deep passes (T = 10).  Up to T = 8 the time of a step hardly depends on the number of time levels it advances
+// (T = 6 -> 8 costs 2 %: the step is bound by its synchronisation / latency chain), so more levels per step are
+// cheap throughput as long as the state fits the register file: 10 levels need 168 registers, i.e. bands of at
+// most 384 floats.  Measured per SWEEP (profiles/r1_sweep_bands_T8_T10_T12.txt): T = 10 is 4 % faster than T = 8 at
+// 4K, 2 % at 1080p, equal at 720p and slower below; T = 12 is slower everywhere (10.6 vs 6.95 us at 1080p: the
+// 24-step unrolled body no longer fits the instruction cache) and is not built.
+template <int T>
+static int launch_stream_deep(const float* coefA, const float* coefB, const float* u_src, float* u_dst,
+    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
+{
+    const int L = 3 * W, sms = sm_count();
+    constexpr int NCAND = 2;   // 448 floats: 146 registers per thread, T = 10 spills
+    const int cands[NCAND] = {384, 256};
+    int best = 0;
+    StreamGeom bg = stream_geom(T, cands[0], L, H, sms);
+    if (g_stream_band >= 1 && g_stream_band <= 4) {
+        best = g_stream_band == 4 ? 1 : 0;
+        bg = stream_geom(T, cands[best], L, H, sms);
+    } else {
+        for (int i = 1; i < NCAND; ++i) {
+            const StreamGeom g = stream_geom(T, cands[i], L, H, sms);
+            if (g.cost < bg.cost) {
+                bg = g;
+                best = i;
+            }
+        }
+    }
+    if (best == 0)
+        return launch_stream<T, 384>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    return launch_stream<T, 256>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+}
+
+// T in {2, 4, 6, 8, 10}; returns VSC_E_INVALID for any other value
 int solver_stream_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
+    if (T == 10)
+        return launch_stream_deep<10>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (T == 8)
         return launch_stream_best<8>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (T == 6)
