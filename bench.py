@@ -359,7 +359,7 @@ def bench_ours(args, rank, world):
         return a.elapsed_time(b)
 
     # the main pass of this image size: 10 sweeps per launch on large images, 8 below (stab_solver.cu, plan_sweeps)
-    T_main = 10 if W * H >= 1500000 else 8
+    T_main = 10 if W * H >= 900000 else 8
     force = args.solver_mode & ~0x3000 | (0x2000 if T_main == 10 else 0x1000)
     n = 16 * T_main
     L.vsc_set_solver_mode(force)

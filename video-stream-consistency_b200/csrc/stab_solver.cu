@@ -189,12 +189,14 @@ static SweepPlan plan_sweeps(int W, int H, int iters)
     SweepPlan p{0, 0, iters, 8};
     // tiny images: the 3T-step pipeline fill and the 6T-float band halo dominate -> plain sweeps
     const bool big = H >= 48 && 3 * W >= 384;
-    if (g_solver_mode == 1 || (g_solver_mode == 0 && !big))
+    // images beyond 2^31 floats: the blocked kernel addresses with 32-bit element offsets
+    const bool fits32 = 3LL * W * (static_cast<long long>(H) + 64) < 0x7fffffffLL;
+    if (g_solver_mode == 1 || !fits32 || (g_solver_mode == 0 && !big))
         return p;  // {0, 0, iters}
-    // 10-sweep passes pay off on large images only (a pass costs 1.21x an 8-sweep pass at >= 1080p, more below),
+    // 10-sweep passes pay off on large images only (a pass costs 1.15-1.22x an 8-sweep pass from 720p up, more below),
     // and only if they save enough passes: 150 = 15 x 10 against 18 x 8 + 6
     auto passes = [&](int t) { return iters / t + (((iters % t) & ~1) ? 1 : 0); };
-    const bool large = static_cast<long long>(W) * H >= 1500000;
+    const bool large = static_cast<long long>(W) * H >= 900000;
     if (g_stream_tmain == 10 || (g_stream_tmain == 0 && large && passes(10) * 121 < passes(8) * 100))
         p.tmain = 10;
     p.n8 = iters / p.tmain;

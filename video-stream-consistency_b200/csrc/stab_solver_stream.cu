@@ -105,22 +105,17 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     // HBM latency (~1-2 us under load) is several steps long: keep PF rows in flight per thread with cp.async
     // into the staging ring; rows (or columns) outside the image are zero-filled (src-size 0: the source is
     // not read, so its address may lie outside the arrays).
-    // Addressing: ONE running per-thread byte offset `boff` = offset of (row y_in, column gi) in any of the
-    // images, advanced by one row per step; the prefetch (PF rows ahead) and store (2T rows behind) row shifts
-    // are folded into CTA-uniform base pointers, so forming an address is a 64-bit add.
+    // Addressing: ONE running per-thread 32-bit ELEMENT offset `eoff` = offset of (row y_in, column gi) in any of
+    // the images, advanced by one row per step (the launcher guarantees that an image plus the pipeline's
+    // look-ahead holds fewer than 2^31 floats); the prefetch (PF rows ahead) and store (2T rows behind) row shifts
+    // are folded into CTA-uniform base pointers, so forming an address is one IMAD.WIDE.
     const unsigned stage_base = static_cast<unsigned>(__cvta_generic_to_shared(stage + tid));
-    const long long row_bytes = static_cast<long long>(L) * 4;
-    long long boff = (static_cast<long long>(r0 - T) * L + static_cast<long long>(colofs)) * 4;
-    const char* const src_o = reinterpret_cast<const char*>(o_src);
-    const char* const src_u = reinterpret_cast<const char*>(u_src);
-    const char* const src_a = reinterpret_cast<const char*>(coefA);
-    const char* const src_b = reinterpret_cast<const char*>(coefB);
-    char* const st_o = reinterpret_cast<char*>(o_dst) - 2 * T * row_bytes;
-    char* const st_u = reinterpret_cast<char*>(u_dst) - 2 * T * row_bytes;
+    int eoff = (r0 - T) * L + static_cast<int>(colofs);
+    float* const st_o = o_dst - 2 * T * L;
+    float* const st_u = u_dst - 2 * T * L;
 
     // ---- private staging (COOP == false): 4 x 4-byte cp.async per thread and row, no cross-thread ordering
-    auto copy_row = [&](const char* bo, const char* bu, const char* ba, const char* bb, long long off, int y,
-                        int slot) {
+    auto copy_row = [&](const float* bo, const float* bu, const float* ba, const float* bb, int off, int y, int slot) {
         const unsigned n = (col_ok && y >= 0 && y < H) ? 4u : 0u;
         const unsigned d = stage_base + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(bo + off), "r"(n) : "memory");
@@ -131,10 +126,10 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                      : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const char* const pf_o = src_o + PF * row_bytes;
-    const char* const pf_u = src_u + PF * row_bytes;
-    const char* const pf_a = src_a + PF * row_bytes;
-    const char* const pf_b = src_b + PF * row_bytes;
+    const float* const pf_o = o_src + PF * L;
+    const float* const pf_u = u_src + PF * L;
+    const float* const pf_a = coefA + PF * L;
+    const float* const pf_b = coefB + PF * L;
 
     // ---- warp-cooperative staging (COOP == true): the 32 columns of a warp x 4 images are 32 chunks of 16 bytes,
     // exactly one per lane: ONE 16-byte cp.async per thread and step instead of four 4-byte ones.  Lane l copies
@@ -147,10 +142,10 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     const int wcol = (tid & ~31) + 4 * (lane & 7);   // first column (inside the band) of my chunk
     const int gcol = g0 + wcol;
     const bool chunk_ok = gcol >= 0 && gcol < L;
-    const char* const my_src = (arr == 0 ? src_o : arr == 1 ? src_u : arr == 2 ? src_a : src_b) + (PF - 1) * row_bytes;
-    long long my_off = (static_cast<long long>(r0 - T) * L + (chunk_ok ? gcol : 0)) * 4;   // row of step s
+    const float* const my_src = (arr == 0 ? o_src : arr == 1 ? u_src : arr == 2 ? coefA : coefB) + (PF - 1) * L;
+    int my_eoff = (r0 - T) * L + (chunk_ok ? gcol : 0);   // row of step s, first column of my chunk
     const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + wcol));
-    auto coop_copy = [&](const char* src, int y, int slot) {
+    auto coop_copy = [&](const float* src, int y, int slot) {
         const unsigned n = (chunk_ok && y >= 0 && y < H) ? 16u : 0u;
         const unsigned d = my_dst + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
@@ -161,11 +156,11 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     if constexpr (COOP) {
 #pragma unroll
         for (int j = 0; j < PF - 1; ++j)   // rows of steps 0 .. PF-2
-            coop_copy(my_src - (PF - 1) * row_bytes + my_off + j * row_bytes, r0 - T + j, j);
+            coop_copy(my_src - (PF - 1) * L + (my_eoff + j * L), r0 - T + j, j);
     } else {
 #pragma unroll
         for (int j = 0; j < PF; ++j)       // rows of steps 0 .. PF-1
-            copy_row(src_o, src_u, src_a, src_b, boff + j * row_bytes, r0 - T + j, j);
+            copy_row(o_src, u_src, coefA, coefB, eoff + j * L, r0 - T + j, j);
     }
     __syncthreads();
 
@@ -223,8 +218,8 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                 if (pub_ok)
                     sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
             } else if (store_col && rho >= r0 && rho < r1) {
-                *reinterpret_cast<float*>(st_o + boff) = on;   // row rho = y_in - 2T
-                *reinterpret_cast<float*>(st_u + boff) = un;
+                st_o[eoff] = on;   // row rho = y_in - 2T
+                st_u[eoff] = un;
             }
         }
         // level 0 arrives: the row of step s was requested PF steps ago.  Waiting is done every second step
@@ -251,13 +246,13 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         }
         if constexpr (COOP) {
             // request the row of step s+PF-1 into the slot this warp read at step s-1
-            coop_copy(my_src + my_off, y_in + PF - 1, (k + PF - 1) % PF);
-            my_off += row_bytes;
+            coop_copy(my_src + my_eoff, y_in + PF - 1, (k + PF - 1) % PF);
+            my_eoff += L;
         } else {
             // refill the slot just consumed (same thread: program order) with the row PF steps ahead
-            copy_row(pf_o, pf_u, pf_a, pf_b, boff, y_in + PF, k % PF);
+            copy_row(pf_o, pf_u, pf_a, pf_b, eoff, y_in + PF, k % PF);
         }
-        boff += row_bytes;
+        eoff += L;
         // ONE barrier per TWO steps: a step reads ring slots (s-2)&3 (and its partner (s-1)&3) and writes
         // slot s&3 (partner (s+1)&3) -- disjoint, and what step s needs was published before the barrier
         // that closed step s-1 (worst-case visibility checked in tests/emul_stream_solver.py, sync_every=2)
@@ -265,18 +260,22 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             ring_sync();
     };
 
+    // The ROWMASK body is the general one; whole groups of U steps take it when any of their steps touches the
+    // image's top or bottom rows, so that the steady-state loop is ONE contiguous run of the mask-free bodies
+    // (the unrolled loop is 34-50 KB of code, more than the 32 KB instruction cache: ncu shows no_instruction
+    // stalls, and interleaving the two bodies step by step spread the hot path over twice the address range).
     for (int base = 0; base < nsteps; base += U) {
+        const int y_first = r0 - T + base;               // y_in of the group's first step
+        const bool edge = y_first <= 2 * T || y_first + U - 1 >= H || base + U > nsteps;
+        if (edge) {
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int s = base + k;
-            if (s < nsteps) {  // uniform across the CTA
-                const int y_in = r0 - T + s;
-                // rows handled this step: y_in-2T .. y_in-2
-                if (y_in <= 2 * T || y_in >= H)
-                    step_body(std::true_type{}, k, y_in);
-                else
-                    step_body(std::false_type{}, k, y_in);
-            }
+            for (int k = 0; k < U; ++k)
+                if (base + k < nsteps)   // uniform across the CTA
+                    step_body(std::true_type{}, k, y_first + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+                step_body(std::false_type{}, k, y_first + k);
         }
     }
 }
@@ -301,9 +300,9 @@ static StreamGeom stream_geom(int T, int BW, int L, int H, int sms)
     g.chunk_rows = (H + nc - 1) / nc;
     g.nc = (H + g.chunk_rows - 1) / g.chunk_rows;
     const long long waves = (static_cast<long long>(g.nb) * g.nc + sms - 1) / sms;
-    // measured time of one step in ns (profiles/r1_sweep_bands*.txt, T = 8, 640x360 ... 4K): not proportional to the
+    // measured time of one step in ns (profiles/r1_sweep_bands_final.txt, T = 8, 640x360 ... 4K): not proportional to the
     // band width -- a narrow band has fewer warps to hide its per-step latency
-    const int step_ns = BW >= 512 ? 450 : BW >= 448 ? 405 : BW >= 384 ? 325 : 258;
+    const int step_ns = BW >= 512 ? 405 : BW >= 448 ? 368 : BW >= 384 ? 315 : 228;
     g.cost = waves * (g.chunk_rows + 3 * T) * step_ns;
     return g;
 }
@@ -411,6 +410,8 @@ static int launch_stream_deep(const float* coefA, const float* coefB, const floa
 int solver_stream_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
+    if (3LL * W * (static_cast<long long>(H) + 64) >= 0x7fffffffLL)   // 32-bit element offsets in the kernel
+        return VSC_E_INVALID;
     if (T == 10)
         return launch_stream_deep<10>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     if (T == 8)
