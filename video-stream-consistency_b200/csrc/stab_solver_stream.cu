@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     // are folded into CTA-uniform base pointers, so forming an address is one IMAD.WIDE.
     const unsigned stage_base = static_cast<unsigned>(__cvta_generic_to_shared(stage + tid));
     int eoff = (r0 - T) * L + static_cast<int>(colofs);
-    float* const st_o = o_dst - 2 * T * L;
-    float* const st_u = u_dst - 2 * T * L;
+    // (row shifts are applied to the 32-bit offset, not to the base pointers: with pre-shifted pointers the
+    // compiler re-associates the sum and forms the address with eight 64-bit instructions instead of three)
+    const int store_shift = 2 * T * L;
 
     // ---- private staging (COOP == false): 4 x 4-byte cp.async per thread and row, no cross-thread ordering
     auto copy_row = [&](const float* bo, const float* bu, const float* ba, const float* bb, int off, int y, int slot) {
@@ -126,10 +127,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                      : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const float* const pf_o = o_src + PF * L;
-    const float* const pf_u = u_src + PF * L;
-    const float* const pf_a = coefA + PF * L;
-    const float* const pf_b = coefB + PF * L;
+    const int pf_shift = PF * L;
 
     // ---- warp-cooperative staging (COOP == true): the 32 columns of a warp x 4 images are 32 chunks of 16 bytes,
     // exactly one per lane: ONE 16-byte cp.async per thread and step instead of four 4-byte ones.  Lane l copies
@@ -142,11 +140,13 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     const int wcol = (tid & ~31) + 4 * (lane & 7);   // first column (inside the band) of my chunk
     const int gcol = g0 + wcol;
     const bool chunk_ok = gcol >= 0 && gcol < L;
-    const float* const my_src = (arr == 0 ? o_src : arr == 1 ? u_src : arr == 2 ? coefA : coefB) + (PF - 1) * L;
-    int my_eoff = (r0 - T) * L + (chunk_ok ? gcol : 0);   // row of step s, first column of my chunk
+    const float* const my_src = arr == 0 ? o_src : arr == 1 ? u_src : arr == 2 ? coefA : coefB;
+    // row of the NEXT request (PF-1 rows ahead of step s), first column of my chunk
+    int my_eoff = (r0 - T + PF - 1) * L + (chunk_ok ? gcol : 0);
     const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + wcol));
-    auto coop_copy = [&](const float* src, int y, int slot) {
-        const unsigned n = (chunk_ok && y >= 0 && y < H) ? 16u : 0u;
+    const unsigned chunk_bytes = chunk_ok ? 16u : 0u;
+    auto coop_copy = [&](const float* src, bool row_ok, int slot) {
+        const unsigned n = row_ok ? chunk_bytes : 0u;   // src-size 0: zero fill, the source is not read
         const unsigned d = my_dst + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     if constexpr (COOP) {
 #pragma unroll
         for (int j = 0; j < PF - 1; ++j)   // rows of steps 0 .. PF-2
-            coop_copy(my_src - (PF - 1) * L + (my_eoff + j * L), r0 - T + j, j);
+            coop_copy(my_src + (my_eoff - (PF - 1 - j) * L), r0 - T + j >= 0 && r0 - T + j < H, j);
     } else {
 #pragma unroll
         for (int j = 0; j < PF; ++j)       // rows of steps 0 .. PF-1
@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                 if (pub_ok)
                     sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
             } else if (store_col && rho >= r0 && rho < r1) {
-                st_o[eoff] = on;   // row rho = y_in - 2T
-                st_u[eoff] = un;
+                const int so = eoff - store_shift;   // row rho = y_in - 2T
+                o_dst[so] = on;
+                u_dst[so] = un;
             }
         }
         // level 0 arrives: the row of step s was requested PF steps ago.  Waiting is done every second step
@@ -246,11 +247,13 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         }
         if constexpr (COOP) {
             // request the row of step s+PF-1 into the slot this warp read at step s-1
-            coop_copy(my_src + my_eoff, y_in + PF - 1, (k + PF - 1) % PF);
+            // (mask-free steps have y_in > 2T: the requested row can only leave the image at the bottom)
+            const int y_req = y_in + PF - 1;
+            coop_copy(my_src + my_eoff, ROWMASK ? (y_req >= 0 && y_req < H) : (y_req < H), (k + PF - 1) % PF);
             my_eoff += L;
         } else {
             // refill the slot just consumed (same thread: program order) with the row PF steps ahead
-            copy_row(pf_o, pf_u, pf_a, pf_b, eoff, y_in + PF, k % PF);
+            copy_row(o_src, u_src, coefA, coefB, eoff + pf_shift, y_in + PF, k % PF);
         }
         eoff += L;
         // ONE barrier per TWO steps: a step reads ring slots (s-2)&3 (and its partner (s-1)&3) and writes
