@@ -251,7 +251,7 @@ class Stabilizer:
         self._keep = []
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:   # `lib` is None while the interpreter shuts down
             lib().vsc_stabilizer_destroy(self._h)
             self._h = C.c_void_p(0)
 
