@@ -53,6 +53,26 @@ __device__ __forceinline__ float hwc_warp_sample1(const float* __restrict__ in, 
     return tmp_1 * ofy + tmp_2 * g.fy;
 }
 
+// the same sample split into its four loads and its arithmetic, so that a kernel can issue the loads of several
+// images back to back (memory-level parallelism) before combining them: identical expression, identical result
+__device__ __forceinline__ void hwc_warp_taps(const float* __restrict__ in, int W, const WarpGeom& g, int c, float t[4])
+{
+    const float* p0 = in + (static_cast<size_t>(g.iy) * W + g.ix) * 3 + c;
+    const float* p1 = p0 + static_cast<size_t>(W) * 3;
+    t[0] = __ldg(p0);
+    t[1] = __ldg(p0 + 3);
+    t[2] = __ldg(p1);
+    t[3] = __ldg(p1 + 3);
+}
+__device__ __forceinline__ float hwc_warp_combine(const float t[4], const WarpGeom& g)
+{
+    const float ofx = 1.0f - g.fx;
+    const float ofy = 1.0f - g.fy;
+    const float tmp_1 = t[0] * ofx + t[1] * g.fx;
+    const float tmp_2 = t[2] * ofx + t[3] * g.fx;
+    return tmp_1 * ofy + tmp_2 * g.fy;
+}
+
 // kernel_adap_comb for one value, flowconsistency.cu:131-164
 __device__ __forceinline__ void adap_comb_value(float ci, float cp, float pi, float pp, float ni, float np, float ls,
     float alpha, float& adp_in, float& adp_pr)

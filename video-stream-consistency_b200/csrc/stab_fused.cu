@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) stage_a_kernel(const float* __restrict__ 
 // and, for pixels with even x and y, also stores (pr, tgt, w) into the half-resolution level-1 inputs: with even
 // W and H the reference's get_bilinear down-scale (flowconsistency.cu:50-75, no half-pixel offset) samples
 // exactly those pixels with weights (1,0,0,0).  Results are bit-identical to the unfused sequence.
-__global__ void __launch_bounds__(256) stage_a_prep_kernel(const float* __restrict__ origPrev,
+__global__ void __launch_bounds__(256, 4) stage_a_prep_kernel(const float* __restrict__ origPrev,
     const float* __restrict__ origCur, const float* __restrict__ origNext, const float* __restrict__ procPrev,
     const float* __restrict__ procCur, const float* __restrict__ procNext, const float* __restrict__ lastStab,
     const float* __restrict__ flowFwd, const float* __restrict__ flowBwd, int flowC, float alpha, float beta,
@@ -77,23 +77,36 @@ __global__ void __launch_bounds__(256) stage_a_prep_kernel(const float* __restri
     const size_t v = p * 3 + c;
     const WarpGeom gb = hwc_warp_geom(ix, iy, __ldg(flowBwd + p * flowC), __ldg(flowBwd + p * flowC + 1), W, H);
     const WarpGeom gf = hwc_warp_geom(ix, iy, __ldg(flowFwd + p * flowC), __ldg(flowFwd + p * flowC + 1), W, H);
-    const float pi = hwc_warp_sample1(origPrev, W, gb, c);
-    const float pp = hwc_warp_sample1(procPrev, W, gb, c);
-    const float ni = hwc_warp_sample1(origNext, W, gf, c);
-    const float np = hwc_warp_sample1(procNext, W, gf, c);
-    const float ls = hwc_warp_sample1(lastStab, W, gb, c);
+    // all 26 loads of the value are issued before the first one is consumed (64 registers, 4 CTAs per SM): the
+    // kernel is bound by gather latency, not by occupancy
+    float t_pi[4], t_pp[4], t_ni[4], t_np[4], t_ls[4];
+    hwc_warp_taps(origPrev, W, gb, c, t_pi);
+    hwc_warp_taps(procPrev, W, gb, c, t_pp);
+    hwc_warp_taps(origNext, W, gf, c, t_ni);
+    hwc_warp_taps(procNext, W, gf, c, t_np);
+    hwc_warp_taps(lastStab, W, gb, c, t_ls);
     const float ci = ldg_stream(origCur + v);
     const float cp = __ldg(procCur + v);
+    const bool has_r = (ix + 1) < (W - 1), has_l = (ix - 1) >= 0, has_d = (iy + 1) < (H - 1), has_u = (iy - 1) >= 0;
+    const float n_r = has_r ? __ldg(procCur + v + 3) : 0.0f;
+    const float n_l = has_l ? __ldg(procCur + v - 3) : 0.0f;
+    const float n_d = has_d ? __ldg(procCur + v + L) : 0.0f;
+    const float n_u = has_u ? __ldg(procCur + v - L) : 0.0f;
+    const float pi = hwc_warp_combine(t_pi, gb);
+    const float pp = hwc_warp_combine(t_pp, gb);
+    const float ni = hwc_warp_combine(t_ni, gf);
+    const float np = hwc_warp_combine(t_np, gf);
+    const float ls = hwc_warp_combine(t_ls, gb);
     float ai, tgt;
     adap_comb_value(ci, cp, pi, pp, ni, np, ls, alpha, ai, tgt);
     const float w = consist_wt_value(ci, ai, beta, gamma);
     // Laplacian of the processed frame with the reference's inclusion tests (flowconsistency.cu:215-238)
     int cnt = 0;
     float lap = 0.0f;
-    if ((ix + 1) < (W - 1)) { lap += __ldg(procCur + v + 3); cnt += 1; }
-    if ((ix - 1) >= 0)      { lap += __ldg(procCur + v - 3); cnt += 1; }
-    if ((iy + 1) < (H - 1)) { lap += __ldg(procCur + v + L); cnt += 1; }
-    if ((iy - 1) >= 0)      { lap += __ldg(procCur + v - L); cnt += 1; }
+    if (has_r) { lap += n_r; cnt += 1; }
+    if (has_l) { lap += n_l; cnt += 1; }
+    if (has_d) { lap += n_d; cnt += 1; }
+    if (has_u) { lap += n_u; cnt += 1; }
     lap -= static_cast<float>(cnt) * cp;
     coefA[v] = -step * (static_cast<float>(cnt) + w);
     coefB[v] = step * (w * tgt - lap);
