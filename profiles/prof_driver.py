@@ -66,7 +66,10 @@ if "warp" in which:
     for (C, h, w) in ((32, 544, 960), (64, 272, 480), (96, 136, 240), (64, 72, 120)):
         x = rnd(1, C, h, w)
         f = torch.from_numpy(synth.op_flow_smooth(1, h, w, 3)).to(dev)
-        for _ in range(2):
-            V.warp(x, f)
+        for mode in (1, 2):   # linear, tiled
+            V.check(V.lib().vsc_set_warp_mode(mode))
+            for _ in range(2):
+                V.warp(x, f)
+        V.lib().vsc_set_warp_mode(0)
         torch.cuda.synchronize()
 print("prof_driver done, launches:", V.launch_count())

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_tiled_kerne
         __stcs(op, sample(pt, pb));
 }
 
-int g_warp_mode = 0;  // 0 auto (by map size), 1 linear one-pixel-per-thread kernel, 2 tiled
+int g_warp_mode = 0;  // 0 default (= 1), 1 linear one-pixel-per-thread kernel, 2 tiled
 
 }  // namespace vsc
 
@@ -240,9 +240,10 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
         return VSC_E_INVALID;
     if (!aligned4(in) || !aligned4(flow) || !aligned4(out))
         return VSC_E_ALIGN;
-    // measured (profiles/r1_time_ops_v13.txt): the tiled kernel wins on the large levels (up to 10 % with
-    // scattered flow), the linear one on the small ones, where fewer, fuller CTAs matter more
-    if (g_warp_mode == 2 || (g_warp_mode == 0 && static_cast<long long>(H) * W >= 131072)) {
+    // measured (profiles/r1_time_ops_v13.txt, r1_warp_linear_vs_tiled_ncu.txt): on smooth flow -- what an optical-flow
+    // network produces -- the linear kernel is 4-16 % faster at every level shape; the tiled one wins only on
+    // scattered flow (i.i.d. sigma = 2 px: 53 vs 59 us at 32x544x960).  Default: linear; tiled on request.
+    if (g_warp_mode == 2) {
         const unsigned tx = cdiv(W, kWarpTileW), ty = cdiv(H, kWarpTileH);
         const long long tiles = static_cast<long long>(tx) * ty * N;
         const long long want = 4LL * sm_count() * 8;
