@@ -102,8 +102,8 @@ VSC_API int vsc_warp_nchw_f32(const float* in, const float* flow, float* out, in
     vsc_stream_t stream);
 
 /* Kernel selection for vsc_warp_nchw_f32 (same results): 0 default (= 1), 1 = one pixel per thread over the
- * flattened image (fastest on smooth flow), 2 = 32x8 pixel tiles with a shared 2x2 gather quad (faster on
- * scattered flow).  Process-wide; for tests and benchmarks. */
+* flattened image (fastest on smooth flow), 2 = 32x8 pixel tiles with a shared 2x2 gather quad (faster on
+ * scattered flow), 3 = the quad addressing on the flattened mapping.  Process-wide; for tests and benchmarks. */
 VSC_API int vsc_set_warp_mode(int mode);
 
 /* ------------------------------------------------------------------ stabilization (HWC fp32, 3 channels)

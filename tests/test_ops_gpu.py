@@ -108,7 +108,7 @@ def test_correlation_full_size_properties(V, dev):
 
 
 # ---------------------------------------------------------------- Warp
-@pytest.fixture(params=[1, 2], ids=["linear", "tiled"])
+@pytest.fixture(params=[1, 2, 3], ids=["linear", "tiled", "linear-quad"])
 def warp_mode(V, request):
     """every Warp test runs on both kernels (vsc_set_warp_mode)"""
     assert V.lib().vsc_set_warp_mode(request.param) == 0
@@ -184,10 +184,13 @@ def test_warp_kernels_agree(V, dev):
             a = V.warp(x, f)
             assert V.lib().vsc_set_warp_mode(2) == 0
             b = V.warp(x, f)
+            assert V.lib().vsc_set_warp_mode(3) == 0
+            c = V.warp(x, f)
         finally:
             V.lib().vsc_set_warp_mode(0)
         assert torch.equal(a, b), (N, C, H, W)
-    assert V.lib().vsc_set_warp_mode(3) == -1
+        assert torch.equal(a, c), (N, C, H, W)
+    assert V.lib().vsc_set_warp_mode(4) == -1
 
 
 def test_ops_reject_bad_arguments(V, dev):

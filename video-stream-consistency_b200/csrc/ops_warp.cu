@@ -169,13 +169,25 @@ __device__ __forceinline__ WarpQuad warp_quad(int x, int y, float fu, float fv, 
 // warp stores one 128-byte row segment per channel, and the bottom taps of a row are the top taps of the row
 // below it in the same CTA, so they hit in L1 instead of going back to L2.
 constexpr int kWarpTileW = 32, kWarpTileH = 8;
-__global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_tiled_kernel(const float* __restrict__ in,
+// TILED: grid x = 32-pixel column tiles, y = 8-row tiles; otherwise grid x = 256-pixel groups of the flattened
+// image, y = 1 (the linear kernel's mapping with the quad's cheaper addressing); z = n * channel chunks.
+template <bool TILED>
+__global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_quad_kernel(const float* __restrict__ in,
     const float* __restrict__ flow, float* __restrict__ out, int C, int H, int W, int chunk, int nchunk)
 {
-    const int x = blockIdx.x * kWarpTileW + (threadIdx.x & (kWarpTileW - 1));
-    const int y = blockIdx.y * kWarpTileH + (threadIdx.x / kWarpTileW);
-    if (x >= W || y >= H)
-        return;
+    int x, y;
+    if constexpr (TILED) {
+        x = blockIdx.x * kWarpTileW + (threadIdx.x & (kWarpTileW - 1));
+        y = blockIdx.y * kWarpTileH + (threadIdx.x / kWarpTileW);
+        if (x >= W || y >= H)
+            return;
+    } else {
+        const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+        if (pp >= H * W)
+            return;
+        y = pp / W;
+        x = pp - y * W;
+    }
     const int HW = H * W;
     const int n = blockIdx.z / nchunk;
     const int c0 = (blockIdx.z - n * nchunk) * chunk;
@@ -243,8 +255,10 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     // measured (profiles/r1_time_ops_v13.txt, r1_warp_linear_vs_tiled_ncu.txt): on smooth flow -- what an optical-flow
     // network produces -- the linear kernel is 4-16 % faster at every level shape; the tiled one wins only on
     // scattered flow (i.i.d. sigma = 2 px: 53 vs 59 us at 32x544x960).  Default: linear; tiled on request.
-    if (g_warp_mode == 2) {
-        const unsigned tx = cdiv(W, kWarpTileW), ty = cdiv(H, kWarpTileH);
+    if (g_warp_mode >= 2) {
+        const bool tiled = g_warp_mode == 2;
+        const unsigned tx = tiled ? cdiv(W, kWarpTileW) : cdiv(static_cast<long long>(H) * W, 256);
+        const unsigned ty = tiled ? cdiv(H, kWarpTileH) : 1;
         const long long tiles = static_cast<long long>(tx) * ty * N;
         const long long want = 4LL * sm_count() * 8;
         int nchunk = static_cast<int>((want + tiles - 1) / tiles);
@@ -256,8 +270,11 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
         if (ty > 65535 || static_cast<long long>(N) * nchunk > 65535)
             return VSC_E_INVALID;
         const dim3 grid(tx, ty, static_cast<unsigned>(N * nchunk));
-        warp_nchw_tiled_kernel<<<grid, kWarpTileW * kWarpTileH, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk,
-            nchunk);
+        if (tiled)
+            warp_nchw_quad_kernel<true><<<grid, kWarpTileW * kWarpTileH, 0, as_stream(stream)>>>(in, flow, out, C, H, W,
+                chunk, nchunk);
+        else
+            warp_nchw_quad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk, nchunk);
         count_launch();
         return launch_status();
     }
@@ -279,7 +296,7 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
 
 extern "C" int vsc_set_warp_mode(int mode)
 {
-    if (mode < 0 || mode > 2)
+    if (mode < 0 || mode > 3)
         return VSC_E_INVALID;
     vsc::g_warp_mode = mode;
     return VSC_OK;
