@@ -225,20 +225,24 @@ constexpr int kWThreads = 384;                         // 128 pixel quads x 3 di
 constexpr int kWStageFloats = kKC * (kWASize + kWBSize);  // 13312 floats = 52 KB
 constexpr unsigned kWStageBytes = kWStageFloats * sizeof(float);
 
+// Persistent: gridDim.x = min(tiles, SMs) CTAs walk the tiles (tile = blockIdx.x + i * gridDim.x) with ONE
+// continuous chunk counter, so the loads of the next tile's first channel chunks are already in flight while
+// the 108 accumulators of the current tile are being stored (with 32-64 channels a tile has only 4-8 chunks:
+// without this the TMA fill and the store drain of every tile were exposed).
 __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
     const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out, int C,
-    int H, int W, float divisor, int legacy, int vec_store)
+    int H, int W, float divisor, int legacy, int vec_store, int tiles_x, int tiles_y, int ntiles)
 {
     extern __shared__ __align__(128) unsigned char smem_bytes[];
     float* stage_mem = reinterpret_cast<float*>(smem_bytes);
     __shared__ __align__(8) unsigned long long bars[2 * kStages];  // full[0..2], empty[0..2]
 
     const int tid = threadIdx.x;
-    const int w0 = blockIdx.x * kWTW;
-    const int h0 = blockIdx.y * kTH;
-    const int n = blockIdx.z;
     const int nchunks = (C + kKC - 1) / kKC;
     const unsigned bar0 = smem_u32(bars);
+    // my tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int my_tiles = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int total = my_tiles * nchunks;   // chunks this CTA consumes, numbered G = 0 .. total-1
 
     if (tid == 0) {
 #pragma unroll
@@ -250,8 +254,19 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
     }
     __syncthreads();
 
-    auto issue = [&](int j) {  // thread 0 only: TMA for channel chunk j into stage j % kStages
-        const int s = j % kStages;
+    auto tile_coords = [&](int it, int& w0, int& h0, int& n) {
+        const int t = blockIdx.x + it * gridDim.x;
+        const int bx = t % tiles_x;
+        const int rest = t / tiles_x;
+        w0 = bx * kWTW;
+        h0 = (rest % tiles_y) * kTH;
+        n = rest / tiles_y;
+    };
+    auto issue = [&](int G) {  // thread 0 only: TMA for global chunk G into stage G % kStages
+        int w0, h0, n;
+        tile_coords(G / nchunks, w0, h0, n);
+        const int j = G % nchunks;
+        const int s = G % kStages;
         const unsigned full = bar0 + 8 * s;
         mbar_expect_tx(full, kWStageBytes);
         const unsigned dstA = smem_u32(stage_mem + s * kWStageFloats);
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
     };
     if (tid == 0) {
         issue(0);
-        if (nchunks > 1)
+        if (total > 1)
             issue(1);
     }
 
@@ -270,61 +285,68 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
     const int r = q >> 4;           // tile row 0..7
     const int qc = (q & 15) * 4;    // first tile column of the quad
     float acc[3][kP][4];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < kP; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                acc[i][j][k] = 0.0f;
 
-    for (int j = 0; j < nchunks; ++j) {
-        const int s = j % kStages;
-        if (tid == 0 && j + 2 < nchunks) {  // refill the stage consumed at iteration j-1
-            if (j >= 1)
-                mbar_wait(bar0 + 8 * (kStages + (j + 2) % kStages), ((j + 2) / kStages - 1) & 1);
-            issue(j + 2);
-        }
-        mbar_wait(bar0 + 8 * s, (j / kStages) & 1);
-        const float* sA = stage_mem + s * kWStageFloats + r * kWTW + qc;
-        const float* sB = stage_mem + s * kWStageFloats + kKC * kWASize + (r + 3 * g) * kWBW + qc;
-        // software pipeline: the next 128-bit in2 load is in flight while the current one feeds 16 FMAs
-        float4 bn = *reinterpret_cast<const float4*>(sB);
-        float4 an = *reinterpret_cast<const float4*>(sA);
+    int G = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < kP; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[i][j][k] = 0.0f;
+
+        for (int j = 0; j < nchunks; ++j, ++G) {
+            const int s = G % kStages;
+            if (tid == 0 && G + 2 < total) {  // refill the stage consumed at iteration G-1 (possibly for the next tile)
+                if (G >= 1)
+                    mbar_wait(bar0 + 8 * (kStages + (G + 2) % kStages), ((G + 2) / kStages - 1) & 1);
+                issue(G + 2);
+            }
+            mbar_wait(bar0 + 8 * s, (G / kStages) & 1);
+            const float* sA = stage_mem + s * kWStageFloats + r * kWTW + qc;
+            const float* sB = stage_mem + s * kWStageFloats + kKC * kWASize + (r + 3 * g) * kWBW + qc;
+            // software pipeline: the next 128-bit in2 load is in flight while the current one feeds 16 FMAs
+            float4 bn = *reinterpret_cast<const float4*>(sB);
+            float4 an = *reinterpret_cast<const float4*>(sA);
 #pragma unroll 1
-        for (int c = 0; c < kKC; ++c) {
-            const float av[4] = {an.x, an.y, an.z, an.w};
-            if (c + 1 < kKC)
-                an = *reinterpret_cast<const float4*>(sA + (c + 1) * kWASize);
+            for (int c = 0; c < kKC; ++c) {
+                const float av[4] = {an.x, an.y, an.z, an.w};
+                if (c + 1 < kKC)
+                    an = *reinterpret_cast<const float4*>(sA + (c + 1) * kWASize);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+                for (int i = 0; i < 3; ++i) {
 #pragma unroll
-                for (int h = 0; h < 3; ++h) {
-                    const float bv[4] = {bn.x, bn.y, bn.z, bn.w};
-                    // address of the load after (c, i, h)
-                    const int hn = (h + 1) % 3;
-                    const int in_ = (h == 2) ? (i + 1) % 3 : i;
-                    const bool wrap = (h == 2 && i == 2);
-                    if (!wrap || c + 1 < kKC)
-                        bn = *reinterpret_cast<const float4*>(sB + (c + (wrap ? 1 : 0)) * kWBSize + in_ * kWBW + 4 * hn);
+                    for (int h = 0; h < 3; ++h) {
+                        const float bv[4] = {bn.x, bn.y, bn.z, bn.w};
+                        // address of the load after (c, i, h)
+                        const int hn = (h + 1) % 3;
+                        const int in_ = (h == 2) ? (i + 1) % 3 : i;
+                        const bool wrap = (h == 2 && i == 2);
+                        if (!wrap || c + 1 < kKC)
+                            bn = *reinterpret_cast<const float4*>(
+                                sB + (c + (wrap ? 1 : 0)) * kWBSize + in_ * kWBW + 4 * hn);
 #pragma unroll
-                    for (int mm = 0; mm < 4; ++mm) {
-                        const int m = 4 * h + mm;
+                        for (int mm = 0; mm < 4; ++mm) {
+                            const int m = 4 * h + mm;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int jj = m - k;
-                            if (jj >= 0 && jj < kP)
-                                acc[i][jj][k] = __fmaf_rn(av[k], bv[mm], acc[i][jj][k]);
+                            for (int k = 0; k < 4; ++k) {
+                                const int jj = m - k;
+                                if (jj >= 0 && jj < kP)
+                                    acc[i][jj][k] = __fmaf_rn(av[k], bv[mm], acc[i][jj][k]);
+                            }
                         }
                     }
                 }
             }
+            __syncwarp();
+            if ((tid & 31) == 0)
+                mbar_arrive(bar0 + 8 * (kStages + s));
         }
-        __syncwarp();
-        if ((tid & 31) == 0)
-            mbar_arrive(bar0 + 8 * (kStages + s));
+        int w0, h0, n;
+        tile_coords(it, w0, h0, n);
+        correlation_store(out, acc, n, g, h0 + r, w0 + qc, H, W, divisor, legacy, vec_store);
     }
-    correlation_store(out, acc, n, g, h0 + r, w0 + qc, H, W, divisor, legacy, vec_store);
 }
 
 // ---- plain-load stager for shapes TMA cannot address (W % 4 != 0 or unaligned bases) ----------------
@@ -569,9 +591,13 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
                 static unsigned long long configured = 0;
                 if (const int e = ensure_dynamic_smem(correlation_md4_tma64_kernel, smem, false, configured))
                     return e;
-                const dim3 gridw(cdiv(W, kWTW), cdiv(H, kTH), N);
-                correlation_md4_tma64_kernel<<<gridw, kWThreads, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
-                    legacy ? 1 : 0, vec);
+                const int tiles_x = static_cast<int>(cdiv(W, kWTW)), tiles_y = static_cast<int>(cdiv(H, kTH));
+                const long long ntiles = static_cast<long long>(tiles_x) * tiles_y * N;
+                if (ntiles > 0x7fffffffLL)
+                    return VSC_E_INVALID;
+                const unsigned ctas = static_cast<unsigned>(ntiles < sm_count() ? ntiles : sm_count());
+                correlation_md4_tma64_kernel<<<ctas, kWThreads, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
+                    legacy ? 1 : 0, vec, tiles_x, tiles_y, static_cast<int>(ntiles));
                 count_launch();
                 return launch_status();
             }
