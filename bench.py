@@ -534,12 +534,22 @@ def main():
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        res = bench_reference(args, rank, world)
-    else:
-        res = bench_ours(args, rank, world)
+    # stdout carries exactly ONE line, the JSON result: anything a library prints while the benchmark runs (NCCL's
+    # version banner at communicator creation, compiler chatter) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            res = bench_reference(args, rank, world)
+        else:
+            res = bench_ours(args, rank, world)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if rank == 0 and res is not None:
-        print(json.dumps(res))
+        print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":
