@@ -217,9 +217,15 @@ extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flo
         if (!rc)
             rc = cu(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     };
-    if (!rc) rc = cu(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
-    if (!rc) rc = cu(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
-    if (!rc) rc = cu(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
+    // The compute stream gets the highest priority, the copy streams the lowest: a solver pass fills every SM
+    // (one CTA each, all registers), so the conversion kernels of the frame being uploaded can only start when a
+    // pass retires -- with equal priorities they then delay the next pass; with low priority they wait for the
+    // level-1 passes, whose narrower CTAs leave half of each SM free.
+    int prio_lo = 0, prio_hi = 0;
+    if (!rc) rc = cu(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // lo = numerically greatest
+    if (!rc) rc = cu(cudaStreamCreateWithPriority(&s->compute, cudaStreamNonBlocking, prio_hi));
+    if (!rc) rc = cu(cudaStreamCreateWithPriority(&s->copy, cudaStreamNonBlocking, prio_lo));
+    if (!rc) rc = cu(cudaStreamCreateWithPriority(&s->d2h, cudaStreamNonBlocking, prio_lo));
     for (int k = 0; k < kSlots; ++k) {
         dmalloc(reinterpret_cast<void**>(&s->orig[k]), fb);
         dmalloc(reinterpret_cast<void**>(&s->proc[k]), fb);
