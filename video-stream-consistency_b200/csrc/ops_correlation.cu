@@ -623,11 +623,18 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
     const size_t per_n = static_cast<size_t>(P) * P * H * W;
     if (max_displacement == kMD && static_cast<long long>(H) * W * kP * kP < 0x7fffffffLL) {
         const dim3 grids(cdiv(static_cast<long long>(kP) * H * W, 32), N);
-        if (static_cast<long long>(grids.x) * N < 2LL * sm_count() && C >= 64)
+        // channel slices per CTA: about 16 channels per warp (shorter slices drown in the per-task set-up and the
+        // shared-memory reduction, longer ones serialise the DRAM round trips), 16 slices when the grid alone
+        // cannot fill the SMs
+        const bool tiny = static_cast<long long>(grids.x) * N < 2LL * sm_count() && C >= 64;
+        if (tiny || C >= 160)
             correlation_md4_rows_kernel<16><<<grids, 32 * 16, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
                 legacy ? 1 : 0);
-        else
+        else if (C >= 96)
             correlation_md4_rows_kernel<8><<<grids, 32 * 8, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
+                legacy ? 1 : 0);
+        else
+            correlation_md4_rows_kernel<4><<<grids, 32 * 4, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
                 legacy ? 1 : 0);
         count_launch();
         return launch_status();
