@@ -138,8 +138,8 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  *   1  unblocked sweeps only;   2  blocked passes whenever numIter >= 4, whatever the image size.
  * Two flag bits select variants of the blocked kernel (same results): | 0x10 = CTA-wide barrier instead of
  * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging;
- * | 0x40 = vsc_frame_stabilize never takes its fused path; | 0x80 = blocked passes launched without programmatic
- * dependent launch; | (j << 12), j = 1 or 2: main blocked passes always of 8 / always of 10 sweeps
+ * | 0x40 = vsc_frame_stabilize never takes its fused path; | 0x80 = no programmatic dependent launch
+ * anywhere in the library; | (j << 12), j = 1 or 2: main blocked passes always of 8 / always of 10 sweeps
  * (default: 10 on images of at least 0.9 Mpx when that saves passes, else 8); | (k << 8), k = 1..4, forces the band width of the
  * blocked kernel (512, 448, 384, 256 floats) instead of the cost model.
  * Process-wide; meant for tests and benchmarks. */

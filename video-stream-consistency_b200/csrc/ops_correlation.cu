@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
     const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out, int C,
     int H, int W, float divisor, int legacy, int vec_store, int tiles_x, int tiles_y, int ntiles)
 {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_bytes[];
     float* stage_mem = reinterpret_cast<float*>(smem_bytes);
     __shared__ __align__(8) unsigned long long bars[2 * kStages];  // full[0..2], empty[0..2]
@@ -446,6 +447,7 @@ template <int kSplitC>
 __global__ void __launch_bounds__(32 * kSplitC) correlation_md4_rows_kernel(const float* __restrict__ in1,
     const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float scale, int use_div)
 {
+    pdl_enter();
     __shared__ float part[kSplitC][kP][32];
     __shared__ int obase[32];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -596,10 +598,10 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
                 if (ntiles > 0x7fffffffLL)
                     return VSC_E_INVALID;
                 const unsigned ctas = static_cast<unsigned>(ntiles < sm_count() ? ntiles : sm_count());
-                correlation_md4_tma64_kernel<<<ctas, kWThreads, smem, st>>>(mapA, mapB, out, C, H, W, divisor,
-                    legacy ? 1 : 0, vec, tiles_x, tiles_y, static_cast<int>(ntiles));
+                const int rc = launch_pdl(correlation_md4_tma64_kernel, dim3(ctas), dim3(kWThreads), smem, st, mapA, mapB,
+                    out, C, H, W, divisor, legacy ? 1 : 0, vec, tiles_x, tiles_y, static_cast<int>(ntiles));
                 count_launch();
-                return launch_status();
+                return rc ? rc : launch_status();
             }
         }
         if (tma_ok) {
@@ -627,15 +629,17 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
         // shared-memory reduction, longer ones serialise the DRAM round trips), 16 slices when the grid alone
         // cannot fill the SMs
         const bool tiny = static_cast<long long>(grids.x) * N < 2LL * sm_count() && C >= 64;
+        const float fC = static_cast<float>(C);
+        const int lg = legacy ? 1 : 0;
+        int rc;
         if (tiny || C >= 160)
-            correlation_md4_rows_kernel<16><<<grids, 32 * 16, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
-                legacy ? 1 : 0);
+            rc = launch_pdl(correlation_md4_rows_kernel<16>, grids, dim3(32 * 16), 0, st, in1, in2, out, C, H, W, fC, lg);
         else if (C >= 96)
-            correlation_md4_rows_kernel<8><<<grids, 32 * 8, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
-                legacy ? 1 : 0);
+            rc = launch_pdl(correlation_md4_rows_kernel<8>, grids, dim3(32 * 8), 0, st, in1, in2, out, C, H, W, fC, lg);
         else
-            correlation_md4_rows_kernel<4><<<grids, 32 * 4, 0, st>>>(in1, in2, out, C, H, W, static_cast<float>(C),
-                legacy ? 1 : 0);
+            rc = launch_pdl(correlation_md4_rows_kernel<4>, grids, dim3(32 * 4), 0, st, in1, in2, out, C, H, W, fC, lg);
+        if (rc)
+            return rc;
         count_launch();
         return launch_status();
     }

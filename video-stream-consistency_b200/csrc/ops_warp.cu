@@ -88,6 +88,7 @@ __device__ __forceinline__ float warp_sample(const float* __restrict__ plane, co
 __global__ void __launch_bounds__(256) warp_nchw_kernel(const float* __restrict__ in, const float* __restrict__ flow,
     float* __restrict__ out, int C, int H, int W, int chunk)
 {
+    pdl_enter();
     const int HW = H * W;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW)
@@ -289,9 +290,9 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     chunk = (chunk + 3) / 4 * 4;  // whole unrolled groups
     nchunk = (C + chunk - 1) / chunk;
     const dim3 grid(gx, nchunk, N);
-    warp_nchw_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, flow, out, C, H, W, chunk);
+    const int rc = launch_pdl(warp_nchw_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }
 
 extern "C" int vsc_set_warp_mode(int mode)

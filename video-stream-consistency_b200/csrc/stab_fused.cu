@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256, 4) stage_a_prep_kernel(const float* __res
     float gamma, float step, float* __restrict__ coefA, float* __restrict__ coefB, float* __restrict__ pr1,
     float* __restrict__ tg1, float* __restrict__ wt1, int W, int H)
 {
+    pdl_enter();
     const int L = 3 * W;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float index inside the row
     const int iy = blockIdx.y;
@@ -124,10 +125,10 @@ int launch_stage_a_prep(const float* origPrev, const float* origCur, const float
     float* wt1, int W, int H, cudaStream_t st)
 {
     const dim3 grid(cdiv(3LL * W, 256), H);
-    stage_a_prep_kernel<<<grid, 256, 0, st>>>(origPrev, origCur, origNext, procPrev, procCur, procNext, lastStab,
-        flowFwd, flowBwd, flowC, alpha, beta, gamma, step, coefA, coefB, pr1, tg1, wt1, W, H);
+    const int rc = launch_pdl(stage_a_prep_kernel, grid, dim3(256), 0, st, origPrev, origCur, origNext, procPrev, procCur,
+        procNext, lastStab, flowFwd, flowBwd, flowC, alpha, beta, gamma, step, coefA, coefB, pr1, tg1, wt1, W, H);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }
 
 }  // namespace vsc

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) consist_wt_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) bilinear_kernel(const float* __restrict__ in, int Wi, int Hi, int Ci,
     float* __restrict__ out, int Wo, int Ho, int Co)
 {
+    pdl_enter();
     const int ox = blockIdx.x * blockDim.x + threadIdx.x;
     const int oy = blockIdx.y;
     if (ox >= Wo)
@@ -119,6 +120,7 @@ template <int C>
 __global__ void __launch_bounds__(256) bilinear_up2_kernel(const float* __restrict__ in, int Wi, int Hi,
     float* __restrict__ out)
 {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // float index inside the input row
     const int iy = blockIdx.y;
     if (i >= Wi * C)
@@ -181,6 +183,7 @@ __device__ __forceinline__ unsigned char f32_to_u8(float v)
 __global__ void __launch_bounds__(256) f32x3_to_rgba8_kernel(const float* __restrict__ in, uchar4* __restrict__ out,
     size_t P)
 {
+    pdl_enter();
     const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (p >= P)
         return;
@@ -253,17 +256,15 @@ extern "C" int vsc_bilinear(const float* in, int Wi, int Hi, int Ci, float* out,
     if (Wo == 2 * Wi && Ho == 2 * Hi && Ci == Co && (Co == 3 || Co == 2) && static_cast<long long>(Wo) * Wi <= (1 << 24)
         && static_cast<long long>(Ho) * Hi <= (1 << 24) && static_cast<long long>(Wi) * Ci < (1 << 29)) {
         const dim3 grid2(cdiv(static_cast<long long>(Wi) * Co, 256), Hi);
-        if (Co == 3)
-            bilinear_up2_kernel<3><<<grid2, 256, 0, as_stream(stream)>>>(in, Wi, Hi, out);
-        else
-            bilinear_up2_kernel<2><<<grid2, 256, 0, as_stream(stream)>>>(in, Wi, Hi, out);
+        const int rc = Co == 3 ? launch_pdl(bilinear_up2_kernel<3>, grid2, dim3(256), 0, as_stream(stream), in, Wi, Hi, out)
+                               : launch_pdl(bilinear_up2_kernel<2>, grid2, dim3(256), 0, as_stream(stream), in, Wi, Hi, out);
         count_launch();
-        return launch_status();
+        return rc ? rc : launch_status();
     }
     const dim3 grid(cdiv(Wo, 256), Ho);
-    bilinear_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, Wi, Hi, Ci, out, Wo, Ho, Co);
+    const int rc = launch_pdl(bilinear_kernel, grid, dim3(256), 0, as_stream(stream), in, Wi, Hi, Ci, out, Wo, Ho, Co);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }
 
 // Device-side input path for the flow network.  FlowModel::run scales the three window frames on
@@ -277,6 +278,7 @@ namespace vsc {
 __global__ void __launch_bounds__(256) rgba8_scale_nearest_kernel(const uchar4* __restrict__ src, int sw, int sh,
     uchar4* __restrict__ dst, int dw, int dh, unsigned ix, unsigned iy)
 {
+    pdl_enter();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= dw)
@@ -300,10 +302,10 @@ extern "C" int vsc_rgba8_scale_nearest(const uint8_t* src_dev, int srcW, int src
     const unsigned iy = static_cast<unsigned>(65536.0 * static_cast<double>(srcH) / static_cast<double>(dstH));
     // (ix / 2 + x * ix) must fit 32 bits: x * ix < dstW * 65536 * srcW / dstW = 65536 * srcW <= 2^31
     const dim3 grid(cdiv(dstW, 256), dstH);
-    rgba8_scale_nearest_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uchar4*>(src_dev), srcW, srcH,
-        reinterpret_cast<uchar4*>(dst_dev), dstW, dstH, ix, iy);
+    const int rc = launch_pdl(rgba8_scale_nearest_kernel, grid, dim3(256), 0, as_stream(stream),
+        reinterpret_cast<const uchar4*>(src_dev), srcW, srcH, reinterpret_cast<uchar4*>(dst_dev), dstW, dstH, ix, iy);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }
 
 extern "C" int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, int H, vsc_stream_t stream)
@@ -326,7 +328,8 @@ extern "C" int vsc_f32x3_to_rgba8(const float* in, uint8_t* rgba_dev, int W, int
     if (!aligned4(rgba_dev))
         return VSC_E_ALIGN;
     const size_t P = static_cast<size_t>(W) * H;
-    f32x3_to_rgba8_kernel<<<cdiv(P, 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<uchar4*>(rgba_dev), P);
+    const int rc = launch_pdl(f32x3_to_rgba8_kernel, dim3(cdiv(P, 256)), dim3(256), 0, as_stream(stream), in,
+        reinterpret_cast<uchar4*>(rgba_dev), P);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) solver_prepare_kernel(const float* __rest
     const float* __restrict__ tgt, const float* __restrict__ wt, float* __restrict__ coefA, float* __restrict__ coefB,
     float* __restrict__ u, const float* __restrict__ copy_src, float* __restrict__ copy_dst, int W, int H, float step)
 {
+    pdl_enter();
     const int L = 3 * W;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) solver_sweep_vec_kernel(const float* __re
     const float* __restrict__ coefB, float* __restrict__ u, const float* __restrict__ src, float* __restrict__ dst,
     int W, int H, float step, float mom)
 {
+    pdl_enter();
     const int L = 3 * W;
     const int L4 = L >> 2;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256) solver_sweep_scalar_kernel(const float* _
     const float* __restrict__ coefB, float* __restrict__ u, const float* __restrict__ src, float* __restrict__ dst,
     int W, int H, float step, float mom)
 {
+    pdl_enter();
     const int L = 3 * W;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -160,9 +163,10 @@ static int launch_prepare(const float* pr, const float* tgt, const float* wt, co
     const float* copy_src, float* copy_dst, int W, int H, float step, cudaStream_t st)
 {
     const dim3 grid(cdiv(3LL * W, 256), H);
-    solver_prepare_kernel<<<grid, 256, 0, st>>>(pr, tgt, wt, b.coefA, b.coefB, b.u, copy_src, copy_dst, W, H, step);
+    const int rc = launch_pdl(solver_prepare_kernel, grid, dim3(256), 0, st, pr, tgt, wt, b.coefA, b.coefB, b.u, copy_src,
+        copy_dst, W, H, step);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }
 
 // implemented in stab_solver_stream.cu: T sweeps per launch, T in {8, 4}
@@ -172,7 +176,6 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
 extern int g_stream_band;
-extern bool g_stream_pdl;
 bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
 int g_stream_tmain = 0;                     // sweeps per main blocked pass: 0 = chosen per solve, else 8 or 10
@@ -229,11 +232,14 @@ static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, i
     for (int k = 0; k < plan.rest; ++k) {
         if (vec) {
             const dim3 grid(cdiv(3LL * W / 4, 128), H);
-            solver_sweep_vec_kernel<<<grid, 128, 0, st>>>(b.coefA, b.coefB, us, src, dst, W, H, step, mom);
+            rc = launch_pdl(solver_sweep_vec_kernel, grid, dim3(128), 0, st, b.coefA, b.coefB, us, src, dst, W, H, step, mom);
         } else {
             const dim3 grid(cdiv(3LL * W, 256), H);
-            solver_sweep_scalar_kernel<<<grid, 256, 0, st>>>(b.coefA, b.coefB, us, src, dst, W, H, step, mom);
+            rc = launch_pdl(solver_sweep_scalar_kernel, grid, dim3(256), 0, st, b.coefA, b.coefB, us, src, dst, W, H, step,
+                mom);
         }
+        if (rc)
+            return rc;
         float* t = src;
         src = dst;
         dst = t;
@@ -286,7 +292,7 @@ extern "C" int vsc_set_solver_mode(int mode)
     g_stream_pair = (mode & 0x10) == 0;
     g_stream_coop = (mode & 0x20) == 0;
     g_frame_fused = (mode & 0x40) == 0;
-    g_stream_pdl = (mode & 0x80) == 0;
+    g_pdl = (mode & 0x80) == 0;
     g_stream_tmain = ((mode >> 12) & 3) == 0 ? 0 : 6 + 2 * ((mode >> 12) & 3);
     g_stream_band = (mode >> 8) & 7;
     return VSC_OK;

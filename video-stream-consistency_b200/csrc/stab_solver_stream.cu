@@ -37,7 +37,6 @@ __host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 :
 __host__ __device__ constexpr int stream_halo(int T) { return (3 * T + 3) / 4 * 4; }
 bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
 bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
-bool g_stream_pdl = true;           // programmatic dependent launch: pass n+1's prologue overlaps pass n's tail
 int g_stream_band = 0;              // 0 = cost model; 1..4 force a band candidate (benchmarks, vsc_set_solver_mode)
 
 // BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best.
@@ -328,7 +327,7 @@ static int launch_stream_impl(const StreamGeom& g, const float* coefA, const flo
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_stream_pdl ? 1 : 0;
+    cfg.numAttrs = g_pdl ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_stream_kernel<T, BW, COOP, SYNC>, coefA, coefB, u_src, u_dst,
         o_src, o_dst, W, H, g.chunk_rows, step, mom);
     count_launch();

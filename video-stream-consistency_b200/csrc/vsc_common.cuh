@@ -53,6 +53,34 @@ inline int ensure_dynamic_smem(Kernel kernel, size_t smem, bool max_carveout, un
     return VSC_OK;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may start while its predecessor in
+// the stream is still draining; it must call pdl_wait() before it touches anything the predecessor wrote (the
+// wait returns once the predecessor grid has completed and flushed), and it calls pdl_trigger() first so that ITS
+// successor can be placed early as well.  Without the launch attribute both are no-ops, so the kernels can also be
+// launched the ordinary way.  The per-frame chain is ~45 dependent launches: this hides their launch latencies.
+extern bool g_pdl;   // vsc_set_solver_mode(| 0x80) turns it off (A/B runs)
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    return e == cudaSuccess ? VSC_OK : static_cast<int>(e);
+}
+
 // streaming (read-once) loads/stores: do not allocate in L1
 __device__ __forceinline__ float4 ldg_stream4(const float* p)
 {
