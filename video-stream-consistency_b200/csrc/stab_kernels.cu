@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) bilinear_up2_kernel(const float* __restri
 __global__ void __launch_bounds__(256) rgba8_to_f32x3_kernel(const uchar4* __restrict__ in, float* __restrict__ out,
     size_t P)
 {
+    pdl_enter();
     __shared__ float tile[768];
     const size_t p0 = static_cast<size_t>(blockIdx.x) * 256;
     const size_t p = p0 + threadIdx.x;
@@ -315,10 +316,10 @@ extern "C" int vsc_rgba8_to_f32x3(const uint8_t* rgba_dev, float* out, int W, in
     if (!aligned4(rgba_dev))
         return VSC_E_ALIGN;
     const size_t P = static_cast<size_t>(W) * H;
-    rgba8_to_f32x3_kernel<<<cdiv(P, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uchar4*>(rgba_dev), out,
-        P);
+    const int rc = launch_pdl(rgba8_to_f32x3_kernel, dim3(cdiv(P, 256)), dim3(256), 0, as_stream(stream),
+        reinterpret_cast<const uchar4*>(rgba_dev), out, P);
     count_launch();
-    return launch_status();
+    return rc ? rc : launch_status();
 }
 
 extern "C" int vsc_f32x3_to_rgba8(const float* in, uint8_t* rgba_dev, int W, int H, vsc_stream_t stream)
