@@ -55,14 +55,17 @@ __device__ __forceinline__ float hwc_warp_sample1(const float* __restrict__ in, 
 
 // the same sample split into its four loads and its arithmetic, so that a kernel can issue the loads of several
 // images back to back (memory-level parallelism) before combining them: identical expression, identical result
+// (32-bit element offsets -- the launchers guarantee images of fewer than 2^31 floats -- so that an address is one
+// IMAD.WIDE plus immediates instead of a 64-bit multiply-add chain: the fused kernel is instruction-bound, and
+// address arithmetic was as many instructions as its floating-point work)
 __device__ __forceinline__ void hwc_warp_taps(const float* __restrict__ in, int W, const WarpGeom& g, int c, float t[4])
 {
-    const float* p0 = in + (static_cast<size_t>(g.iy) * W + g.ix) * 3 + c;
-    const float* p1 = p0 + static_cast<size_t>(W) * 3;
-    t[0] = __ldg(p0);
-    t[1] = __ldg(p0 + 3);
-    t[2] = __ldg(p1);
-    t[3] = __ldg(p1 + 3);
+    const int o0 = (g.iy * W + g.ix) * 3 + c;
+    const int o1 = o0 + 3 * W;
+    t[0] = __ldg(in + o0);
+    t[1] = __ldg(in + o0 + 3);
+    t[2] = __ldg(in + o1);
+    t[3] = __ldg(in + o1 + 3);
 }
 __device__ __forceinline__ float hwc_warp_combine(const float t[4], const WarpGeom& g)
 {

@@ -74,10 +74,11 @@ __global__ void __launch_bounds__(256, 4) stage_a_prep_kernel(const float* __res
         return;
     const int ix = i / 3;
     const int c = i - 3 * ix;
-    const size_t p = static_cast<size_t>(iy) * W + ix;
-    const size_t v = p * 3 + c;
-    const WarpGeom gb = hwc_warp_geom(ix, iy, __ldg(flowBwd + p * flowC), __ldg(flowBwd + p * flowC + 1), W, H);
-    const WarpGeom gf = hwc_warp_geom(ix, iy, __ldg(flowFwd + p * flowC), __ldg(flowFwd + p * flowC + 1), W, H);
+    const int p = iy * W + ix;      // 32-bit element offsets: the launcher checks 3*W*H < 2^31
+    const int v = p * 3 + c;
+    const int pf = p * flowC;
+    const WarpGeom gb = hwc_warp_geom(ix, iy, __ldg(flowBwd + pf), __ldg(flowBwd + pf + 1), W, H);
+    const WarpGeom gf = hwc_warp_geom(ix, iy, __ldg(flowFwd + pf), __ldg(flowFwd + pf + 1), W, H);
     // all 26 loads of the value are issued before the first one is consumed (64 registers, 4 CTAs per SM): the
     // kernel is bound by gather latency, not by occupancy
     float t_pi[4], t_pp[4], t_ni[4], t_np[4], t_ls[4];
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256, 4) stage_a_prep_kernel(const float* __res
     coefA[v] = -step * (static_cast<float>(cnt) + w);
     coefB[v] = step * (w * tgt - lap);
     if (((ix | iy) & 1) == 0) {
-        const size_t v1 = (static_cast<size_t>(iy >> 1) * (W >> 1) + (ix >> 1)) * 3 + c;
+        const int v1 = ((iy >> 1) * (W >> 1) + (ix >> 1)) * 3 + c;
         pr1[v1] = cp;
         tg1[v1] = tgt;
         wt1[v1] = w;

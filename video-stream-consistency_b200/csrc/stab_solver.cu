@@ -480,7 +480,8 @@ extern "C" int vsc_frame_stabilize(const float* origPrev, const float* origCur, 
         return VSC_E_WORKSPACE;
     if (level_dims(W, H, levels).w[levels - 1] < 1 || level_dims(W, H, levels).h[levels - 1] < 1)
         return VSC_E_INVALID;
-    const bool fused = levels == 2 && (W % 2 == 0) && (H % 2 == 0) && g_frame_fused;
+    // (the fused kernel addresses with 32-bit element offsets)
+    const bool fused = levels == 2 && (W % 2 == 0) && (H % 2 == 0) && g_frame_fused && 3LL * W * H < 0x7fffffffLL;
     if (fused) {
         const StageAInputs in{origPrev, origCur, origNext, procPrev, procNext, lastStab, flowFwd, flowBwd,
             flow_channels};
