@@ -61,10 +61,15 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     constexpr int PF = COOP ? U : stream_private_pf(T);  // staging ring depth (rows in flight from HBM)
     static_assert(BW % 64 == 0 && U % PF == 0 && PF >= 4, "staging geometry: slot index = step mod PF = k mod PF");
     extern __shared__ float smem_raw[];
-    float* sm = smem_raw + 4;  // 4 floats of padding on each side: tid-3 / tid+3 never leave the allocation
+    // exchange ring: T*4 rows of RW = BW + 8 floats.  The 8 floats between two rows (4 behind one row, 4 before the
+    // next) are never written: the band's first / last three threads read their out-of-band neighbours tid-3 /
+    // tid+3 there and get 0.0f (their columns are halo either way; without the padding they read another row's
+    // live values -- harmless, but a nondeterministic read that compute-sanitizer rightly reports as a hazard)
+    constexpr int RW = BW + 8;
+    float* sm = smem_raw + 4;
     // thread-private staging ring for the level-0 rows: stage[slot][array][tid], filled by cp.async PF steps
     // ahead (each thread copies and later reads only its own 4 floats per row: no cross-thread ordering needed)
-    float* stage = smem_raw + T * 4 * BW + 8;
+    float* stage = smem_raw + T * 4 * RW + 8;
 
     // Programmatic dependent launch: let the next pass of the stream start placing its CTAs as ours retire (its
     // prologue -- index set-up, zeroing of the exchange ring -- then overlaps our tail); it blocks in
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     }
     // the ring slots read before they are first written belong to the invalid cone; zero them so that no
     // NaN/Inf garbage is ever combined (finite garbage is harmless: it never reaches a stored value)
-    for (int i = tid; i < T * 4 * BW + 8; i += BW)
+    for (int i = tid; i < T * 4 * RW + 8; i += BW)
         smem_raw[i] = 0.0f;
 
     // HBM latency (~1-2 us under load) is several steps long: keep PF rows in flight per thread with cp.async
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             const float c = win[t - 1][(k + 2) & 3];   // produced at step s-2
             float up = win[t - 1][(k + 1) & 3];        // s-3
             float dn = win[t - 1][(k + 3) & 3];        // s-1
-            const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * BW + tid;
+            const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * RW + tid;
             const float lf = row[-3];
             const float rt = row[3];
             if constexpr (ROWMASK) {
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
                 win[t % T][k & 3] = on;   // (t % T only silences the bounds warning for t == T)
                 uu[t % T][k & 3] = un;
                 if (pub_ok)
-                    sm[((t % T) * 4 + (k & 3)) * BW + tid] = on;
+                    sm[((t % T) * 4 + (k & 3)) * RW + tid] = on;
             } else if (store_col && rho >= r0 && rho < r1) {
                 const int so = eoff - store_shift;   // row rho = y_in - 2T
                 o_dst[so] = on;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
             win[0][k & 3] = n_o;
             uu[0][k & 3] = st[BW];
             if (pub_ok)
-                sm[(k & 3) * BW + tid] = n_o;
+                sm[(k & 3) * RW + tid] = n_o;
             Ar[k % U] = st[2 * BW];
             Br[k % U] = st[3 * BW];
         }
@@ -314,7 +319,7 @@ static int launch_stream_impl(const StreamGeom& g, const float* coefA, const flo
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     constexpr int PF = COOP ? 2 * T : stream_private_pf(T);
-    const size_t smem = (static_cast<size_t>(T) * 4 * BW + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(T) * 4 * (BW + 8) + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static unsigned long long configured = 0;
     if (const int e = ensure_dynamic_smem(solver_stream_kernel<T, BW, COOP, SYNC>, smem, false, configured))
         return e;
