@@ -428,11 +428,14 @@ def cpu_frame(O, wl, band_h, state):
     """one frame (or a horizontal band of it) of the hot path on the host: reference CPU custom ops
     (oracle/_ref, the reference's own kernels, 1 thread as built) + the oracle port of the stabilization
     (the reference has no CPU stabilization code), OpenMP over all cores."""
+    # the 14 op calls of a frame are independent of each other: run them on a thread pool (ctypes releases the GIL),
+    # so that the reference's single-threaded CPU kernels still use all host cores
+    jobs = []
     for d in range(2):
-        for a, b in state["corr"][d]:
-            state["corr_fn"](a, b)
-        for x, f in state["warp"][d]:
-            state["warp_fn"](x, f)
+        jobs += [(state["corr_fn"], a, b) for a, b in state["corr"][d]]
+        jobs += [(state["warp_fn"], x, f) for x, f in state["warp"][d]]
+    if jobs:
+        list(state["pool"].map(lambda j: j[0](j[1], j[2]), jobs))
     of, pf, ff, fb = state["of"], state["pf"], state["ff"], state["fb"]
     co, _ = O.do_one_step(of[0], of[1], of[2], pf[0], pf[1], pf[2], state["last"], ff, fb)
     state["last"] = co
@@ -450,7 +453,11 @@ def cpu_state(O, wl, band_h):
     use_ref = O.ref_cpu_available()
     st["corr_fn"] = O.ref_cpu_correlation if use_ref else O.correlation
     st["warp_fn"] = O.ref_cpu_warp if use_ref else O.warp_nchw
-    st["ops_kind"] = "reference (oracle/_ref, 1 thread as built)" if use_ref else "oracle port"
+    st["ops_kind"] = ("reference (oracle/_ref; its kernels are single-threaded as built, the independent op calls of a "
+                      "frame run concurrently on a thread pool)") if use_ref else "oracle port"
+    from concurrent.futures import ThreadPoolExecutor
+
+    st["pool"] = ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1))
     frac = band_h / wl["H"]
     st["corr"], st["warp"] = [], []
     for d in range(2):
