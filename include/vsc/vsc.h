@@ -133,8 +133,9 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
     vsc_stream_t stream);
 
 /* How the sweeps are executed (results are identical, bit for bit, in every mode):
- *   0  auto (default): temporally blocked passes (8 / 4 sweeps per launch, intermediate sweeps kept on chip)
- *      for images of at least 128x48, single unblocked sweeps otherwise and for the numIter % 4 remainder;
+ *   0  auto (default): temporally blocked passes (10 or 8 sweeps per launch plus one shorter even pass,
+ *      intermediate sweeps kept on chip) for images of at least 128x48, single unblocked sweeps otherwise and
+ *      for an odd remainder;
  *   1  unblocked sweeps only;   2  blocked passes whenever numIter >= 4, whatever the image size.
  * Two flag bits select variants of the blocked kernel (same results): | 0x10 = CTA-wide barrier instead of
  * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging;
