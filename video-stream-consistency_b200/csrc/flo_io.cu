@@ -71,10 +71,11 @@ int flo_read_into(const char* path, float* dst, size_t cap_floats, int* width, i
             std::fclose(f);
             return have < 12 + bytes ? VSC_E_FLO_SHORT : VSC_E_FLO_LONG;   // :67-69, :72-74
         }
-        unsigned nt = std::thread::hardware_concurrency();
-        nt = nt >= 8 ? 4 : (nt >= 4 ? 2 : 1);
+        // two files of a frame are read concurrently (stabilizer.cu): half the cores each, at most 8
+        unsigned nt = std::thread::hardware_concurrency() / 2;
+        nt = nt > 8 ? 8 : (nt < 1 ? 1 : nt);
         const size_t part = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
-        bool ok[4] = {true, true, true, true};
+        bool ok[8] = {true, true, true, true, true, true, true, true};
         auto work = [&](unsigned k) {
             size_t off = k * part;
             const size_t end = off + part < bytes ? off + part : bytes;
@@ -88,7 +89,7 @@ int flo_read_into(const char* path, float* dst, size_t cap_floats, int* width, i
                 off += static_cast<size_t>(got);
             }
         };
-        std::thread th[3];
+        std::thread th[7];
         for (unsigned k = 1; k < nt; ++k)
             th[k - 1] = std::thread(work, k);
         work(0);
