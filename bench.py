@@ -223,6 +223,7 @@ def bench_ours(args, rank, world):
     sets = make_op_tensors(wl, dev)
     hpar = V.HyperParams()
     V.check(V.lib().vsc_set_solver_mode(args.solver_mode))
+    V.check(V.lib().vsc_set_stage_a_mode(args.stage_a_mode))
 
     # ---------------- device-resident arm: every input already in HBM ----------------
     d_o = [V.image_to_gpu(x.to(dev)) for x in ho]
@@ -379,6 +380,32 @@ def bench_ours(args, rank, world):
     except Exception:
         pass
 
+    # the fused stage-A kernel (5 warps + adaptive combination + consistency weight in one pass) timed alone through
+    # vsc_stage_a_fused, CUDA events over 16 launches cycling the frame pairs (each launch reads 7 images + 2 flows:
+    # more than L2 at both resolutions).  Algorithmic bytes 132 B/pixel.
+    f_full = [d_flf, d_flb] if (fw, fh) == (W, H) else [V.get_bilinear(d_flf, W, H), V.get_bilinear(d_flb, W, H)]
+    sa_out = [torch.empty_like(d_p[0]) for _ in range(2)]
+
+    def stage_a_once(i):
+        a, b, c = i % NFRAMES, (i + 1) % NFRAMES, (i + 2) % NFRAMES
+        V.check(L.vsc_stage_a_fused(dptr(d_o[a]), dptr(d_o[b]), dptr(d_o[c]), dptr(d_p[a]), dptr(d_p[b]), dptr(d_p[c]),
+                                    dptr(last), dptr(f_full[0]), dptr(f_full[1]), flow_c, C.c_float(hpar.alpha),
+                                    C.c_float(hpar.beta), C.c_float(hpar.gamma), None, dptr(sa_out[0]), dptr(sa_out[1]),
+                                    W, H, stream()))
+    for i in range(3):
+        stage_a_once(i)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for i in range(16):
+        stage_a_once(i)
+    eb.record()
+    torch.cuda.synchronize()
+    stage_a_ms = ea.elapsed_time(eb) / 16
+    stage_a_bytes = (120.0 + 4.0 * 2 * flow_c) * W * H   # 7 images read + 2 flows + 2 images written (+ 3rd flow channel)
+    stage_a_gbs = stage_a_bytes / (stage_a_ms * 1e-3) / 1e9
+    del f_full, sa_out
+
     # ---------------- aggregate over ranks (max time) ----------------
     (ms_res, ms_e2e), (launches,) = reduce_over_ranks([ms_res, ms_e2e], [launches], world, dev)
 
@@ -413,7 +440,11 @@ def bench_ours(args, rank, world):
                                  f"{T_main - 1} of {T_main} sweeps on chip, so achieved may exceed the HBM peak (see "
                                  "traffic for DRAM bytes)",
                          "unblocked_sweep": {"kernel": "solver_sweep_vec_kernel", "achieved": unblocked,
-                                             "frac": unblocked / peaks["hbm_gbs"], "us_per_launch": sweep_ms * 1e3}},
+                                             "frac": unblocked / peaks["hbm_gbs"], "us_per_launch": sweep_ms * 1e3},
+                         "fused_stage_a": {"kernel": "stage_a_rows_kernel (warp x5 -> adaptive blend -> weight, one pass)",
+                                           "achieved": stage_a_gbs, "frac": stage_a_gbs / peaks["hbm_gbs"],
+                                           "us_per_launch": stage_a_ms * 1e3,
+                                           "algorithmic_bytes_per_launch": stage_a_bytes}},
         }
         if cpu:
             result["cpu_baseline"] = cpu
@@ -536,6 +567,7 @@ def main():
     ap.add_argument("--workload", default="1080p-light", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solver-mode", type=lambda x: int(x, 0), default=0, help="vsc_set_solver_mode value (A/B runs)")
+    ap.add_argument("--stage-a-mode", type=lambda x: int(x, 0), default=0, help="vsc_set_stage_a_mode value (A/B runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -103,7 +103,10 @@ VSC_API int vsc_warp_nchw_f32(const float* in, const float* flow, float* out, in
 
 /* Kernel selection for vsc_warp_nchw_f32 (same results): 0 default (= 1), 1 = one pixel per thread over the
 * flattened image (fastest on smooth flow), 2 = 32x8 pixel tiles with a shared 2x2 gather quad (faster on
- * scattered flow), 3 = the quad addressing on the flattened mapping.  Process-wide; for tests and benchmarks. */
+ * scattered flow), 3 = the quad addressing on the flattened mapping, 4 = the linear kernel walking over several
+ * 256-pixel groups per CTA with the next group's flow prefetched (| (j << 12): 2^j groups, default 4);
+ * | (k << 4), k = 1..255: the linear kernels split the channels into k chunks (grid y) instead of choosing the split
+ * themselves.  Process-wide; for tests and benchmarks. */
 VSC_API int vsc_set_warp_mode(int mode);
 
 /* ------------------------------------------------------------------ stabilization (HWC fp32, 3 channels)
@@ -165,6 +168,13 @@ VSC_API int vsc_stage_a_fused(const float* origPrev, const float* origCur, const
     const float* procPrev, const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd,
     const float* flowBwd, int flow_channels, float alpha, float beta, float gamma, float* adapCmbIn, float* adapCmbPr,
     float* consWt, int W, int H, vsc_stream_t stream);
+
+/* Kernel selection for the fused stage A (vsc_stage_a_fused, vsc_frame_stabilize, the stream object; same results
+ * bit for bit).  Low 4 bits: 0 default (= 3 with 128-thread CTAs), 1 = one row per CTA, 2 = a thread walks down a
+ * chunk of rows, 3 = + the next row's flow prefetched, 4 = + the next row's loads issued before the current row's
+ * arithmetic; bits 4-7 = log2(rows per CTA) (0 = 8, fewer on small frames); | 0x100 = 128-thread CTAs.
+ * vsc_stage_a_fused itself only distinguishes 1 from the rest.  Process-wide; for tests and benchmarks. */
+VSC_API int vsc_set_stage_a_mode(int mode);
 
 /* hyperParams of the reference, same field order (videostabilizer.h:38-46) */
 typedef struct vsc_hyper_params {

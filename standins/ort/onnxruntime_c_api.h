@@ -22,6 +22,7 @@
 enum ONNXTensorElementDataType {
     ONNX_TENSOR_ELEMENT_DATA_TYPE_UNDEFINED = 0,
     ONNX_TENSOR_ELEMENT_DATA_TYPE_FLOAT = 1,
+    ONNX_TENSOR_ELEMENT_DATA_TYPE_UINT8 = 2,
     ONNX_TENSOR_ELEMENT_DATA_TYPE_INT64 = 7,
     ONNX_TENSOR_ELEMENT_DATA_TYPE_DOUBLE = 11
 };

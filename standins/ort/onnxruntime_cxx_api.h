@@ -130,3 +130,5 @@ struct CustomOpBase : OrtCustomOp {
 };
 
 }  // namespace Ort
+
+#include "onnxruntime_session_standin.h"   // Env / SessionOptions / IoBinding / Session (flow session)

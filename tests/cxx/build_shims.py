@@ -32,7 +32,14 @@ def build_host_shims(force: bool = False):
     jobs = [(os.path.join(TEST_SO_DIR, "libvsc_ort_shim_test.so"),
              [os.path.join(HERE, "host", "ort_custom_ops", "vsc_custom_ops.cpp"),
               os.path.join(ROOT, "tests", "cxx", "ort_driver.cpp")],
-             ["-I", os.path.join(ROOT, "standins", "ort")], ["-lvsc_b200"])]
+             ["-I", os.path.join(ROOT, "standins", "ort")], ["-lvsc_b200"]),
+            # the flow session (ORT IoBinding on device buffers) + the custom-op library it registers + its driver
+            (os.path.join(TEST_SO_DIR, "libvsc_flow_session_test.so"),
+             [os.path.join(HERE, "host", "inference", "vsc_flow_session.cpp"),
+              os.path.join(HERE, "host", "ort_custom_ops", "vsc_custom_ops.cpp"),
+              os.path.join(ROOT, "tests", "cxx", "flow_session_driver.cpp")],
+             ["-I", os.path.join(ROOT, "standins", "ort"), "-I", CUDA_INC],
+             ["-lvsc_b200", "-L", CUDA_LIB, f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"])]
     if os.path.exists(os.path.join(REF_STAB, "flowconsistency.cuh")):
         jobs.append((os.path.join(TEST_SO_DIR, "libvsc_stab_shim_test.so"),
                      [os.path.join(HERE, "host", "stabilization", "vsc_flowconsistency.cpp"),
@@ -41,7 +48,8 @@ def build_host_shims(force: bool = False):
                      ["-I", REF_STAB, "-I", os.path.join(ROOT, "standins", "qt"), "-I", CUDA_INC],
                      ["-lvsc_b200", "-L", CUDA_LIB, f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"]))
     for out, srcs, inc, libs in jobs:
-        deps = srcs + [LIB]
+        deps = srcs + [LIB] + [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "standins")) for f in fs] \
+            + [os.path.join(HERE, "host", "inference", "vsc_flow_session.h")]
         if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
             built.append(out)
             continue

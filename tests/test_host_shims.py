@@ -143,3 +143,108 @@ def test_stabilization_shim_sequence(O, dev, W, H):
         if t == 1:
             assert lib.vsc_shim_push(h, o8[3].ctypes.data_as(C.c_void_p), p8[3].ctypes.data_as(C.c_void_p)) == 0
     lib.vsc_shim_destroy(h)
+
+
+# ---------------------------------------------------------------- flow session (ORT IoBinding on device buffers)
+FS_SO = os.path.join(ROOT, "tests", "cxx", "_build", "libvsc_flow_session_test.so")
+
+
+@pytest.fixture(scope="module")
+def fs():
+    if not os.path.exists(FS_SO):
+        pytest.fail(f"{FS_SO} missing: run __graft_entry__.build()")
+    lib = C.CDLL(FS_SO)
+    lib.vsc_fs_test_last_error.restype = C.c_char_p
+    lib.vsc_fs_test_create.restype = C.c_void_p
+    lib.vsc_fs_test_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    lib.vsc_fs_test_destroy.argtypes = [C.c_void_p]
+    lib.vsc_fs_test_stabilizer.restype = C.c_void_p
+    lib.vsc_fs_test_stabilizer.argtypes = [C.c_void_p]
+    lib.vsc_fs_test_step.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vsc_fs_test_flow.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+def _fs_counters(fs):
+    c = (C.c_long * 6)()
+    fs.vsc_fs_test_counters(c)
+    return dict(zip(("runs", "provider_syncs", "sessions", "bound", "graph_calls", "saw_domain"), c))
+
+
+def test_flow_session_library_exports_the_session_entry_points(fs):
+    """CPU: the flow-session test library (product source + stand-in ORT) loads and exports its driver symbols;
+    the product class was compiled against the same Ort:: names the real headers declare."""
+    for name in ("vsc_fs_test_create", "vsc_fs_test_step", "vsc_fs_test_flow", "vsc_fs_test_counters",
+                 "RegisterCustomOps"):
+        assert hasattr(fs, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,scale", [(96, 64, 1), (128, 72, 2), (90, 50, 2)])
+def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale):
+    """FlowModel::run + doOneStep through VscFlowSession: frames pushed from host memory once, the network inputs
+    written on the device (nearest-neighbour scale for FLOWDOWNSCALE), a persistent IoBinding, enqueue-only runs
+    on the stabilizer's stream, flows consumed in place.  The stand-in graph's flow and the stabilized frames must
+    equal the same computation done step by step through the Python binding, bit for bit."""
+    import torch
+
+    netW, netH = W // scale, H // scale
+    T = 6
+    o8, p8 = synth.frames(W, H, T, seed=77)
+    before = _fs_counters(fs)
+    rig = fs.vsc_fs_test_create(W, H, netW, netH, None)
+    assert rig, fs.vsc_fs_test_last_error()
+    st = C.c_void_p(fs.vsc_fs_test_stabilizer(rig))
+    L = V.lib()
+    ref = V.Stabilizer(W, H, 3)
+    outs, refs = [], []
+    try:
+        for t in range(3):
+            assert L.vsc_stabilizer_push_frame(st, o8[t].ctypes.data_as(C.c_void_p), p8[t].ctypes.data_as(C.c_void_p)) == 0
+            ref.push_frame(o8[t], p8[t])
+
+        def graph(first, second):   # what the stand-in model computes, via the Python binding
+            a = V.image_to_gpu(V.rgba8_scale_nearest(torch.from_numpy(first).to(dev), netW, netH))
+            b = V.image_to_gpu(V.rgba8_scale_nearest(torch.from_numpy(second).to(dev), netW, netH))
+            return V.get_warp_result(a, b)
+
+        # one direction on its own, copied back: inputs, binding and output slot are the right ones
+        got = np.empty((netH, netW, 3), np.float32)
+        assert fs.vsc_fs_test_flow(rig, 1, 2, 0, got.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
+        assert np.array_equal(got, graph(o8[1], o8[2]).cpu().numpy())
+        assert fs.vsc_fs_test_flow(rig, 2, 1, 1, got.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
+        assert np.array_equal(got, graph(o8[2], o8[1]).cpu().numpy())
+
+        for t in range(1, T - 1):
+            out = np.zeros((H, W, 4), np.uint8)
+            assert fs.vsc_fs_test_step(rig, out.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
+            assert L.vsc_stabilizer_sync(st) == 0
+            outs.append(out)
+            r = np.zeros((H, W, 4), np.uint8)
+            ref.step(graph(o8[t], o8[t + 1]), graph(o8[t + 1], o8[t]), r)
+            ref.sync()
+            refs.append(r)
+            if t + 2 < T:
+                assert L.vsc_stabilizer_push_frame(st, o8[t + 2].ctypes.data_as(C.c_void_p),
+                                                   p8[t + 2].ctypes.data_as(C.c_void_p)) == 0
+                ref.push_frame(o8[t + 2], p8[t + 2])
+    finally:
+        fs.vsc_fs_test_destroy(rig)
+        ref.close()
+    for a, b in zip(outs, refs):
+        assert np.array_equal(a, b)
+    assert any(np.any(a[..., :3] != p8[i + 1][..., :3]) for i, a in enumerate(outs))   # the step did something
+    c = _fs_counters(fs)
+    steps = T - 2
+    assert c["sessions"] - before["sessions"] == 1
+    assert c["bound"] - before["bound"] == 6                        # 2 persistent bindings x 3 tensors, built once
+    assert c["runs"] - before["runs"] == 2 + 2 * steps              # two directions per frame
+    assert c["provider_syncs"] - before["provider_syncs"] == 0      # every Run was enqueue-only
+    assert c["saw_domain"] == 1                                     # RegisterCustomOps reached the session options
+
+
+@pytest.mark.gpu
+def test_flow_session_unknown_model_throws(fs, V, dev):
+    """InferenceModelVariant::createSession rethrows ORT's load failure (:175-183); so does the flow session."""
+    assert not fs.vsc_fs_test_create(64, 48, 64, 48, b"models/does-not-exist.onnx")
+    assert b"does-not-exist" in fs.vsc_fs_test_last_error()

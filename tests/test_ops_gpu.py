@@ -108,7 +108,7 @@ def test_correlation_full_size_properties(V, dev):
 
 
 # ---------------------------------------------------------------- Warp
-@pytest.fixture(params=[1, 2, 3], ids=["linear", "tiled", "linear-quad"])
+@pytest.fixture(params=[1, 2, 3, 4, 4 | (1 << 12) | (2 << 4)], ids=["linear", "tiled", "linear-quad", "walk", "walk-2groups-2chunks"])
 def warp_mode(V, request):
     """every Warp test runs on both kernels (vsc_set_warp_mode)"""
     assert V.lib().vsc_set_warp_mode(request.param) == 0
@@ -186,11 +186,17 @@ def test_warp_kernels_agree(V, dev):
             b = V.warp(x, f)
             assert V.lib().vsc_set_warp_mode(3) == 0
             c = V.warp(x, f)
+            assert V.lib().vsc_set_warp_mode(4) == 0
+            d = V.warp(x, f)
+            assert V.lib().vsc_set_warp_mode(4 | (3 << 12) | (3 << 4)) == 0   # 8 groups per CTA, 3 channel chunks
+            e = V.warp(x, f)
         finally:
             V.lib().vsc_set_warp_mode(0)
         assert torch.equal(a, b), (N, C, H, W)
         assert torch.equal(a, c), (N, C, H, W)
-    assert V.lib().vsc_set_warp_mode(4) == -1
+        assert torch.equal(a, d), (N, C, H, W)
+        assert torch.equal(a, e), (N, C, H, W)
+    assert V.lib().vsc_set_warp_mode(5) == -1
 
 
 def test_ops_reject_bad_arguments(V, dev):

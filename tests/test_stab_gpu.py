@@ -422,6 +422,48 @@ def test_frame_stabilize_fused_equals_unfused(V, dev, W, H, levels, fc):
     assert torch.equal(got_generic, ref)
 
 
+STAGE_A_MODES = [1, 2 | (1 << 4), 2 | (3 << 4), 3 | (1 << 4), 3 | (2 << 4), 3, 3 | (4 << 4), 3 | (3 << 4) | 0x100,
+                 3 | (3 << 4) | 0x200, 3 | (3 << 4) | 0x400 | 0x100, 4 | (1 << 4), 4 | (2 << 4), 4 | (3 << 4) | 0x100]
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (90, 34), (322, 6), (8, 2), (2, 70), (600, 50)])
+@pytest.mark.parametrize("fc", [3, 2])
+def test_stage_a_kernel_selections_are_bit_identical(V, dev, W, H, fc):
+    """vsc_set_stage_a_mode: the row-walking stage-A kernels (rows carried in registers, flow / loads prefetched)
+    reproduce the one-row-per-CTA kernel bit for bit, for every chunk height incl. chunks taller than the image,
+    ragged last chunks and ragged last CTAs of a row; flow large enough to clamp at every border."""
+    o8, p8 = synth.frames(W, H, 3, seed=41, mismatch=0.3)
+    of = [V.image_to_gpu(cu(x, dev)) for x in o8]
+    pf = [V.image_to_gpu(cu(x, dev)) for x in p8]
+    ff, fb = synth.flows(W, H, fc)
+    rng = np.random.default_rng(5)
+    ff[..., :2] += rng.normal(0, 3.0, ff[..., :2].shape).astype(np.float32)
+    fb[..., :2] += rng.normal(0, 3.0, fb[..., :2].shape).astype(np.float32)
+    ff, fb = cu(ff, dev), cu(fb, dev)
+    last = V.image_to_gpu(cu(p8[0], dev))
+    hp = V.HyperParams(numIter=7)
+    L = V.lib()
+    try:
+        assert L.vsc_set_stage_a_mode(1) == 0
+        ref = V.frame_stabilize(of[0], of[1], of[2], pf[0], pf[1], pf[2], last, ff, fb, hp).clone()
+        refA = [t.clone() for t in V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], last, ff, fb, 6800.0,
+                                                   6800.0, 2.0, want_adap_in=True)]
+        for m in STAGE_A_MODES + [0]:
+            assert L.vsc_set_stage_a_mode(m) == 0
+            got = V.frame_stabilize(of[0], of[1], of[2], pf[0], pf[1], pf[2], last, ff, fb, hp)
+            assert torch.equal(got, ref), hex(m)
+        for m in (0, 3 | (1 << 4), 3 | (5 << 4)):   # the public stage A: row walk vs one row per CTA
+            assert L.vsc_set_stage_a_mode(m) == 0
+            gotA = V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], last, ff, fb, 6800.0, 6800.0, 2.0,
+                                   want_adap_in=True)
+            assert all(torch.equal(a, b) for a, b in zip(gotA, refA)), hex(m)
+    finally:
+        L.vsc_set_stage_a_mode(0)
+    assert L.vsc_set_stage_a_mode(5) == -1
+    assert L.vsc_set_stage_a_mode(0x603) == -1
+    assert L.vsc_set_stage_a_mode(-1) == -1
+
+
 def _write_flo(path, flow2):
     """Middlebury .flo (flowIO.cpp:5-22): 'PIEH', int32 width, int32 height, interleaved float32 u,v rows."""
     h, w, _ = flow2.shape

@@ -119,6 +119,51 @@ __global__ void __launch_bounds__(256) warp_nchw_kernel(const float* __restrict_
 }
 
 
+// The same kernel walking over `groups` consecutive 256-pixel groups per CTA.  warp_nchw_kernel exposes two memory
+// latencies back to back in every thread (flow -> geometry -> taps) and its CTAs live for one pixel group only;
+// here the flow of the next group is already loading while the channels of the current group are gathered
+// (the trick that took the fused stage A from 55 % to 73 % issue utilisation, profiles/r1_stage_a_walk_ncu.txt).
+__global__ void __launch_bounds__(256) warp_nchw_walk_kernel(const float* __restrict__ in,
+    const float* __restrict__ flow, float* __restrict__ out, int C, int H, int W, int chunk, int groups)
+{
+    pdl_enter();
+    const int HW = H * W;
+    int p = blockIdx.x * groups * 256 + threadIdx.x;
+    if (p >= HW)
+        return;
+    const int n = blockIdx.z;
+    const int c0 = blockIdx.y * chunk;
+    const int c1 = min(C, c0 + chunk);
+    const float* fl = flow + static_cast<size_t>(n) * 2 * HW;
+    const float* ip0 = in + (static_cast<size_t>(n) * C + c0) * HW;
+    float* op0 = out + (static_cast<size_t>(n) * C + c0) * HW;
+    float fu = ldg_stream(fl + p), fv = ldg_stream(fl + HW + p);
+    for (int g = 0; g < groups && p < HW; ++g, p += 256) {
+        const int y = p / W;
+        const int x = p - y * W;
+        const WarpTap t = warp_setup(x, y, fu, fv, W, H);
+        if (g + 1 < groups && p + 256 < HW) {
+            fu = ldg_stream(fl + p + 256);
+            fv = ldg_stream(fl + HW + p + 256);
+        }
+        const float* ip = ip0;
+        float* op = op0 + p;
+        int c = c0;
+        for (; c + 4 <= c1; c += 4, ip += 4 * static_cast<size_t>(HW), op += 4 * static_cast<size_t>(HW)) {
+            const float v0 = warp_sample(ip, t);
+            const float v1 = warp_sample(ip + HW, t);
+            const float v2 = warp_sample(ip + 2 * static_cast<size_t>(HW), t);
+            const float v3 = warp_sample(ip + 3 * static_cast<size_t>(HW), t);
+            __stcs(op, v0);
+            __stcs(op + HW, v1);
+            __stcs(op + 2 * static_cast<size_t>(HW), v2);
+            __stcs(op + 3 * static_cast<size_t>(HW), v3);
+        }
+        for (; c < c1; ++c, ip += HW, op += HW)
+            __stcs(op, warp_sample(ip, t));
+    }
+}
+
 // ---- tiled variant ------------------------------------------------------------------------------------------
 // The four taps of a pixel are the 2x2 quad at (xb, yb) = (xL, yT) clamped into the image, so ONE 64-bit address
 // per channel (plus a second one row below) serves all four gathers with constant offsets 0 / +1, instead of four
@@ -239,7 +284,9 @@ __global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_quad_kernel
         __stcs(op, sample(pt, pb));
 }
 
-int g_warp_mode = 0;  // 0 default (= 1), 1 linear one-pixel-per-thread kernel, 2 tiled
+int g_warp_mode = 0;    // 0 default (= 1), 1 linear one-pixel-per-thread kernel, 2 tiled, 3 quad addressing, flattened
+int g_warp_nchunk = 0;  // 0 = automatic channel split of the linear kernel, else the number of channel chunks
+int g_warp_groups = 0;  // kind 4: 256-pixel groups per CTA of the walking kernel (0 = 4)
 
 }  // namespace vsc
 
@@ -256,7 +303,7 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     // measured (profiles/r1_time_ops_v13.txt, r1_warp_linear_vs_tiled_ncu.txt): on smooth flow -- what an optical-flow
     // network produces -- the linear kernel is 4-16 % faster at every level shape; the tiled one wins only on
     // scattered flow (i.i.d. sigma = 2 px: 53 vs 59 us at 32x544x960).  Default: linear; tiled on request.
-    if (g_warp_mode >= 2) {
+    if (g_warp_mode == 2 || g_warp_mode == 3) {
         const bool tiled = g_warp_mode == 2;
         const unsigned tx = tiled ? cdiv(W, kWarpTileW) : cdiv(static_cast<long long>(H) * W, 256);
         const unsigned ty = tiled ? cdiv(H, kWarpTileH) : 1;
@@ -279,26 +326,32 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
         count_launch();
         return launch_status();
     }
-    const unsigned gx = cdiv(static_cast<long long>(H) * W, 256);
+    const int groups = g_warp_mode == 4 ? (g_warp_groups ? g_warp_groups : 4) : 1;
+    const unsigned gx = cdiv(static_cast<long long>(H) * W, 256LL * groups);
     // enough blocks for >= 4 waves of 148 SMs x 8 resident CTAs when the tensor allows, chunks of >= 8 channels
     const long long want = 4LL * sm_count() * 8;
     int nchunk = static_cast<int>((want + static_cast<long long>(gx) * N - 1) / (static_cast<long long>(gx) * N));
     if (nchunk < 1) nchunk = 1;
     if (nchunk > (C + 7) / 8) nchunk = (C + 7) / 8;
+    if (g_warp_nchunk > 0) nchunk = g_warp_nchunk < C ? g_warp_nchunk : C;
     if (nchunk > 65535) nchunk = 65535;
     int chunk = (C + nchunk - 1) / nchunk;
     chunk = (chunk + 3) / 4 * 4;  // whole unrolled groups
     nchunk = (C + chunk - 1) / chunk;
     const dim3 grid(gx, nchunk, N);
-    const int rc = launch_pdl(warp_nchw_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk);
+    const int rc = groups > 1
+        ? launch_pdl(warp_nchw_walk_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk, groups)
+        : launch_pdl(warp_nchw_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk);
     count_launch();
     return rc ? rc : launch_status();
 }
 
 extern "C" int vsc_set_warp_mode(int mode)
 {
-    if (mode < 0 || mode > 3)
+    if (mode < 0 || (mode & 0xF) > 4 || mode > 0xFFFF)
         return VSC_E_INVALID;
-    vsc::g_warp_mode = mode;
+    vsc::g_warp_mode = mode & 0xF;
+    vsc::g_warp_nchunk = (mode >> 4) & 0xFF;
+    vsc::g_warp_groups = (mode >> 12) ? 1 << (mode >> 12) : 0;
     return VSC_OK;
 }

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "vsc_consist_solve": (_i, [_p, _p, _p, _i, _f, _f, _p, _i, _i, _p, _sz, _p]),
     "vsc_set_solver_mode": (_i, [_i]),
     "vsc_set_warp_mode": (_i, [_i]),
+    "vsc_set_stage_a_mode": (_i, [_i]),
     "vsc_rgba8_to_f32x3": (_i, [_p, _p, _i, _i, _p]),
     "vsc_f32x3_to_rgba8": (_i, [_p, _p, _i, _i, _p]),
     "vsc_rgba8_scale_nearest": (_i, [_p, _i, _i, _p, _i, _i, _p]),
