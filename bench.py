@@ -402,7 +402,7 @@ def bench_ours(args, rank, world):
     eb.record()
     torch.cuda.synchronize()
     stage_a_ms = ea.elapsed_time(eb) / 16
-    stage_a_bytes = (120.0 + 4.0 * 2 * flow_c) * W * H   # 7 images read + 2 flows + 2 images written (+ 3rd flow channel)
+    stage_a_bytes = (84.0 + 24.0 + 4.0 * 2 * flow_c) * W * H   # 7 images read, 2 written, 2 flows of flow_c channels
     stage_a_gbs = stage_a_bytes / (stage_a_ms * 1e-3) / 1e9
     del f_full, sa_out
 

@@ -45,6 +45,18 @@ for (W, H) in ((3840, 2160), (1920, 1080)):
         for _ in range(2):
             V.stage_a_fused(*ims, ff, fb, 6800.0, 6800.0, 2.0)
         torch.cuda.synchronize()
+    if "stage_a_prep" in which:   # the stage-A kernel of the frame path (folds into the solver coefficients)
+        o8, p8 = synth.frames(W, H, 3)
+        of = [V.image_to_gpu(torch.from_numpy(x).to(dev)) for x in o8]
+        pf = [V.image_to_gpu(torch.from_numpy(x).to(dev)) for x in p8]
+        ff, fb = (torch.from_numpy(x).to(dev) for x in synth.flows(W, H, 3))
+        for mode in (0, 1):   # default (row walk + flow prefetch), then one row per CTA
+            V.check(V.lib().vsc_set_stage_a_mode(mode))
+            for _ in range(2):
+                V.frame_stabilize(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[0], ff, fb, V.HyperParams(numIter=0))
+        V.lib().vsc_set_stage_a_mode(0)
+        torch.cuda.synchronize()
+        del of, pf, ff, fb
     if "misc" in which:
         img = rnd(H, W, 3)
         for _ in range(2):

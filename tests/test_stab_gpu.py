@@ -423,7 +423,7 @@ def test_frame_stabilize_fused_equals_unfused(V, dev, W, H, levels, fc):
 
 
 STAGE_A_MODES = [1, 2 | (1 << 4), 2 | (3 << 4), 3 | (1 << 4), 3 | (2 << 4), 3, 3 | (4 << 4), 3 | (3 << 4) | 0x100,
-                 3 | (3 << 4) | 0x200, 3 | (3 << 4) | 0x400 | 0x100, 4 | (1 << 4), 4 | (2 << 4), 4 | (3 << 4) | 0x100]
+                 3 | (6 << 4) | 0x100, 4 | (1 << 4), 4 | (2 << 4), 4 | (3 << 4) | 0x100, 4 | (5 << 4)]
 
 
 @pytest.mark.parametrize("W,H", [(64, 48), (90, 34), (322, 6), (8, 2), (2, 70), (600, 50)])
@@ -460,7 +460,7 @@ def test_stage_a_kernel_selections_are_bit_identical(V, dev, W, H, fc):
     finally:
         L.vsc_set_stage_a_mode(0)
     assert L.vsc_set_stage_a_mode(5) == -1
-    assert L.vsc_set_stage_a_mode(0x603) == -1
+    assert L.vsc_set_stage_a_mode(0x203) == -1
     assert L.vsc_set_stage_a_mode(-1) == -1
 
 
