@@ -103,10 +103,8 @@ VSC_API int vsc_warp_nchw_f32(const float* in, const float* flow, float* out, in
 
 /* Kernel selection for vsc_warp_nchw_f32 (same results): 0 default (= 1), 1 = one pixel per thread over the
 * flattened image (fastest on smooth flow), 2 = 32x8 pixel tiles with a shared 2x2 gather quad (faster on
- * scattered flow), 3 = the quad addressing on the flattened mapping, 4 = the linear kernel walking over several
- * 256-pixel groups per CTA with the next group's flow prefetched (| (j << 12): 2^j groups, default 4);
- * | (k << 4), k = 1..255: the linear kernels split the channels into k chunks (grid y) instead of choosing the split
- * themselves.  Process-wide; for tests and benchmarks. */
+ * scattered flow), 3 = the quad addressing on the flattened mapping; | (k << 4), k = 1..255: the linear kernel splits
+ * the channels into k chunks (grid y) instead of choosing the split itself.  Process-wide; for tests and benchmarks. */
 VSC_API int vsc_set_warp_mode(int mode);
 
 /* ------------------------------------------------------------------ stabilization (HWC fp32, 3 channels)

@@ -71,7 +71,7 @@ if NCU:
     MODES = [1] + [3 | (3 << 4) | bs | occ for occ in (0, 0x200, 0x400) for bs in (0, 0x100)] \
         + [3 | (4 << 4) | 0x100 | 0x200, 3 | (4 << 4) | 0x100 | 0x400]
 
-for (W, H) in ((1920, 1080), (3840, 2160)):
+for (W, H) in (() if "--warp" in sys.argv else ((1920, 1080), (3840, 2160))):
     o8, p8 = synth.frames(W, H, 3)
     of = [V.image_to_gpu(torch.from_numpy(o8[t]).to(dev)) for t in range(3)]
     pf = [V.image_to_gpu(torch.from_numpy(p8[t]).to(dev)) for t in range(3)]
@@ -120,8 +120,9 @@ for (W, H) in ((1920, 1080), (3840, 2160)):
     del of, pf, ff, fb, last, ws, out
     torch.cuda.empty_cache()
 
-WARP_MODES = [1, 4 | (1 << 12), 4 | (2 << 12), 4 | (3 << 12), 4 | (2 << 12) | (1 << 4), 4 | (2 << 12) | (2 << 4),
-              4 | (3 << 12) | (1 << 4)]
+# (the walking / shuffle kernels, modes 4 and 5 of the sweeps recorded in r1_stage_a_walk_events2.txt and
+# r1_warp_variants_*.txt, were removed after these measurements)
+WARP_MODES = [1, 3, 2, 1 | (1 << 4), 1 | (2 << 4)]
 g = torch.Generator(device=dev).manual_seed(0)
 if NCU:
     for (C, H, W) in synth.DENSE_4K_WARP[1:]:
@@ -134,8 +135,8 @@ if NCU:
         L.vsc_set_warp_mode(0)
     torch.cuda.synchronize()
 else:
-    print("custom::Warp (us, cold L2): linear auto | walk 2, 4, 8 groups | walk 4 groups 1 chunk, 2 chunks | walk 8 "
-          "groups 1 chunk")
+    print("custom::Warp (us, cold L2), modes " + ", ".join(hex(m) for m in WARP_MODES) + " | torch copy of the same "
+          "tensor (read + write = the op's algorithmic bytes minus the flow)")
     for (C, H, W) in synth.LIGHT_1080P_WARP + synth.DENSE_4K_WARP:
         a = torch.randn((1, C, H, W), device=dev, generator=g)
         fl = torch.from_numpy(synth.op_flow_smooth(1, H, W, 5)).to(dev)
@@ -145,6 +146,7 @@ else:
             assert L.vsc_set_warp_mode(m) == 0
             row.append(timed(lambda: V.warp(a, fl, out=o)))
         L.vsc_set_warp_mode(0)
+        tcopy = timed(lambda: o.copy_(a))
         mb = 4 * H * W * (2 * C + 2) / 1e6
-        print(f"  {C:4d}x{H:4d}x{W:4d}  " + "  ".join(f"{t:6.1f}" for t in row) + f"   {mb:7.1f} MB  best "
+        print(f"  {C:4d}x{H:4d}x{W:4d}  " + "  ".join(f"{t:6.1f}" for t in row) + f"  | copy {tcopy:6.1f}   {mb:7.1f} MB  best "
               f"{mb / min(row) * 1e3:6.0f} GB/s", flush=True)

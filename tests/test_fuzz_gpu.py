@@ -80,7 +80,7 @@ def test_fuzz_warp_kernels_vs_oracle(V, O, dev):
             f = synth.op_flow(N, H, W, 6, float(rng.choice([0.3, 2.0, 30.0])))
             ref = O.warp_nchw(x, f)
             scale = max(float(np.abs(ref).max()), 1e-30)
-            for mode in (1, 2, 3, 4):
+            for mode in (1, 2, 3):
                 assert L.vsc_set_warp_mode(mode) == 0
                 got = V.warp(cu(x, dev), cu(f, dev)).cpu().numpy()
                 assert float(np.abs(got - ref).max()) <= 1e-4 * scale, (N, C, H, W, mode)

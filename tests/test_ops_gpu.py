@@ -108,7 +108,7 @@ def test_correlation_full_size_properties(V, dev):
 
 
 # ---------------------------------------------------------------- Warp
-@pytest.fixture(params=[1, 2, 3, 4, 4 | (1 << 12) | (2 << 4)], ids=["linear", "tiled", "linear-quad", "walk", "walk-2groups-2chunks"])
+@pytest.fixture(params=[1, 2, 3, 1 | (2 << 4)], ids=["linear", "tiled", "linear-quad", "linear-2chunks"])
 def warp_mode(V, request):
     """every Warp test runs on both kernels (vsc_set_warp_mode)"""
     assert V.lib().vsc_set_warp_mode(request.param) == 0
@@ -175,10 +175,17 @@ def test_warp_kernels_agree(V, dev):
     """the tiled kernel (shared 2x2 gather quad, border corners re-slotted) equals the one-pixel-per-thread
     kernel value for value, including every border case a large random flow produces"""
     g = torch.Generator(device=dev).manual_seed(17)
-    for (N, C, H, W) in ((2, 12, 67, 131), (1, 7, 5, 3), (1, 4, 2, 2), (1, 33, 40, 64)):
+    for (N, C, H, W) in ((2, 12, 67, 131), (1, 7, 5, 3), (1, 4, 2, 2), (1, 33, 40, 64), (2, 9, 41, 100), (1, 5, 70, 33)):
         x = torch.randn((N, C, H, W), device=dev, generator=g)
-        f = 6.0 * torch.randn((N, 2, H, W), device=dev, generator=g)
-        f[:, :, ::3, ::2] = torch.round(f[:, :, ::3, ::2])  # integer displacements: alpha/beta exactly 0 at borders
+        if (H, W) in ((41, 100), (70, 33)):
+            # smooth flow: neighbouring lanes sample neighbouring taps (the shuffle kernel's fast path), with a few
+            # NaN / huge displacements so that live and dead lanes alternate inside a warp
+            f = torch.from_numpy(synth.op_flow_smooth(N, H, W, 3, amp=3.0, noise=0.05)).to(dev)
+            f[:, 0, 5::11, 7::13] = float("nan")
+            f[:, 1, 3::7, 2::9] = 1e9
+        else:
+            f = 6.0 * torch.randn((N, 2, H, W), device=dev, generator=g)
+            f[:, :, ::3, ::2] = torch.round(f[:, :, ::3, ::2])  # integer displacements: alpha/beta exactly 0 at borders
         try:
             assert V.lib().vsc_set_warp_mode(1) == 0
             a = V.warp(x, f)
@@ -186,9 +193,9 @@ def test_warp_kernels_agree(V, dev):
             b = V.warp(x, f)
             assert V.lib().vsc_set_warp_mode(3) == 0
             c = V.warp(x, f)
-            assert V.lib().vsc_set_warp_mode(4) == 0
+            assert V.lib().vsc_set_warp_mode(1 | (1 << 4)) == 0   # all channels in one chunk
             d = V.warp(x, f)
-            assert V.lib().vsc_set_warp_mode(4 | (3 << 12) | (3 << 4)) == 0   # 8 groups per CTA, 3 channel chunks
+            assert V.lib().vsc_set_warp_mode(1 | (5 << 4)) == 0   # 5 channel chunks
             e = V.warp(x, f)
         finally:
             V.lib().vsc_set_warp_mode(0)
@@ -196,7 +203,7 @@ def test_warp_kernels_agree(V, dev):
         assert torch.equal(a, c), (N, C, H, W)
         assert torch.equal(a, d), (N, C, H, W)
         assert torch.equal(a, e), (N, C, H, W)
-    assert V.lib().vsc_set_warp_mode(5) == -1
+    assert V.lib().vsc_set_warp_mode(4) == -1
 
 
 def test_ops_reject_bad_arguments(V, dev):

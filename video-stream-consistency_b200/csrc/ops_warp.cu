@@ -85,6 +85,13 @@ __device__ __forceinline__ float warp_sample(const float* __restrict__ plane, co
 // the store is one full 128-byte line (a 4-pixels-per-thread variant with 128-bit stores was measured 4x
 // worse: its gathers stride 16 bytes between lanes, 29 sectors per request -- profiles/r1_notes.md).
 // The channel loop is unrolled 4x: 16 independent gathers in flight per thread.
+// Measured and removed again (profiles/r1_notes.md, r1_warp_variants_ncu.txt; all bit-identical): a CTA walking over
+// 2-8 pixel groups with the next group's flow prefetched (8-16 % slower: fewer, longer CTAs), and right-hand taps
+// taken from the neighbour lane by shuffle instead of a second gather (58 vs 37 us: the shuffle waits for the load,
+// which serialises what were independent gathers).  ncu: 27.75 instructions per value in this loop, 46 per value
+// overall -- 40 % of all instructions are the per-pixel set-up (the reference's double-precision mask arithmetic,
+// p / W) amortised over only 8-16 channels per thread; whole-tensor chunks (vsc_set_warp_mode(1 | 1 << 4)) cut
+// that but leave too few CTAs, and time the same.
 __global__ void __launch_bounds__(256) warp_nchw_kernel(const float* __restrict__ in, const float* __restrict__ flow,
     float* __restrict__ out, int C, int H, int W, int chunk)
 {
@@ -119,50 +126,6 @@ __global__ void __launch_bounds__(256) warp_nchw_kernel(const float* __restrict_
 }
 
 
-// The same kernel walking over `groups` consecutive 256-pixel groups per CTA.  warp_nchw_kernel exposes two memory
-// latencies back to back in every thread (flow -> geometry -> taps) and its CTAs live for one pixel group only;
-// here the flow of the next group is already loading while the channels of the current group are gathered
-// (the trick that took the fused stage A from 55 % to 73 % issue utilisation, profiles/r1_stage_a_walk_ncu.txt).
-__global__ void __launch_bounds__(256) warp_nchw_walk_kernel(const float* __restrict__ in,
-    const float* __restrict__ flow, float* __restrict__ out, int C, int H, int W, int chunk, int groups)
-{
-    pdl_enter();
-    const int HW = H * W;
-    int p = blockIdx.x * groups * 256 + threadIdx.x;
-    if (p >= HW)
-        return;
-    const int n = blockIdx.z;
-    const int c0 = blockIdx.y * chunk;
-    const int c1 = min(C, c0 + chunk);
-    const float* fl = flow + static_cast<size_t>(n) * 2 * HW;
-    const float* ip0 = in + (static_cast<size_t>(n) * C + c0) * HW;
-    float* op0 = out + (static_cast<size_t>(n) * C + c0) * HW;
-    float fu = ldg_stream(fl + p), fv = ldg_stream(fl + HW + p);
-    for (int g = 0; g < groups && p < HW; ++g, p += 256) {
-        const int y = p / W;
-        const int x = p - y * W;
-        const WarpTap t = warp_setup(x, y, fu, fv, W, H);
-        if (g + 1 < groups && p + 256 < HW) {
-            fu = ldg_stream(fl + p + 256);
-            fv = ldg_stream(fl + HW + p + 256);
-        }
-        const float* ip = ip0;
-        float* op = op0 + p;
-        int c = c0;
-        for (; c + 4 <= c1; c += 4, ip += 4 * static_cast<size_t>(HW), op += 4 * static_cast<size_t>(HW)) {
-            const float v0 = warp_sample(ip, t);
-            const float v1 = warp_sample(ip + HW, t);
-            const float v2 = warp_sample(ip + 2 * static_cast<size_t>(HW), t);
-            const float v3 = warp_sample(ip + 3 * static_cast<size_t>(HW), t);
-            __stcs(op, v0);
-            __stcs(op + HW, v1);
-            __stcs(op + 2 * static_cast<size_t>(HW), v2);
-            __stcs(op + 3 * static_cast<size_t>(HW), v3);
-        }
-        for (; c < c1; ++c, ip += HW, op += HW)
-            __stcs(op, warp_sample(ip, t));
-    }
-}
 
 // ---- tiled variant ------------------------------------------------------------------------------------------
 // The four taps of a pixel are the 2x2 quad at (xb, yb) = (xL, yT) clamped into the image, so ONE 64-bit address
@@ -286,7 +249,6 @@ __global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_quad_kernel
 
 int g_warp_mode = 0;    // 0 default (= 1), 1 linear one-pixel-per-thread kernel, 2 tiled, 3 quad addressing, flattened
 int g_warp_nchunk = 0;  // 0 = automatic channel split of the linear kernel, else the number of channel chunks
-int g_warp_groups = 0;  // kind 4: 256-pixel groups per CTA of the walking kernel (0 = 4)
 
 }  // namespace vsc
 
@@ -326,8 +288,7 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
         count_launch();
         return launch_status();
     }
-    const int groups = g_warp_mode == 4 ? (g_warp_groups ? g_warp_groups : 4) : 1;
-    const unsigned gx = cdiv(static_cast<long long>(H) * W, 256LL * groups);
+    const unsigned gx = cdiv(static_cast<long long>(H) * W, 256);
     // enough blocks for >= 4 waves of 148 SMs x 8 resident CTAs when the tensor allows, chunks of >= 8 channels
     const long long want = 4LL * sm_count() * 8;
     int nchunk = static_cast<int>((want + static_cast<long long>(gx) * N - 1) / (static_cast<long long>(gx) * N));
@@ -339,19 +300,16 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     chunk = (chunk + 3) / 4 * 4;  // whole unrolled groups
     nchunk = (C + chunk - 1) / chunk;
     const dim3 grid(gx, nchunk, N);
-    const int rc = groups > 1
-        ? launch_pdl(warp_nchw_walk_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk, groups)
-        : launch_pdl(warp_nchw_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk);
+    const int rc = launch_pdl(warp_nchw_kernel, grid, dim3(256), 0, as_stream(stream), in, flow, out, C, H, W, chunk);
     count_launch();
     return rc ? rc : launch_status();
 }
 
 extern "C" int vsc_set_warp_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 4 || mode > 0xFFFF)
+    if (mode < 0 || (mode & 0xF) > 3 || mode > 0xFFF)
         return VSC_E_INVALID;
     vsc::g_warp_mode = mode & 0xF;
-    vsc::g_warp_nchunk = (mode >> 4) & 0xFF;
-    vsc::g_warp_groups = (mode >> 12) ? 1 << (mode >> 12) : 0;
+    vsc::g_warp_nchunk = mode >> 4;
     return VSC_OK;
 }
