@@ -69,5 +69,19 @@ for (W, H, fc) in ((128, 96, 3), (46, 38, 2)):
     st.step(torch.from_numpy(lf).to(dev), torch.from_numpy(lb).to(dev), out)   # low-res flow: up-scaled inside
     st.sync()
     st.close()
+# fused stage A: every kernel selection (one row per CTA, row walk without / with flow prefetch, pipelined; chunk
+# heights from 2 rows to taller than the image; 128- and 256-thread CTAs), frame path and public entry point
+for (W, H, fc) in ((96, 40, 3), (322, 6, 2), (8, 2, 3)):
+    o8, p8 = synth.frames(W, H, 3, seed=5)
+    of = [V.image_to_gpu(torch.from_numpy(x).to(dev)) for x in o8]
+    pf = [V.image_to_gpu(torch.from_numpy(x).to(dev)) for x in p8]
+    ff, fb = (torch.from_numpy(x + np.random.default_rng(1).normal(0, 3, x.shape).astype(np.float32)).to(dev)
+              for x in synth.flows(W, H, fc))
+    for m in (0, 1, 2 | (1 << 4), 3 | (1 << 4), 3 | (3 << 4) | 0x100, 3 | (6 << 4), 4 | (1 << 4), 4 | (2 << 4) | 0x100,
+              4 | (6 << 4)):
+        V.check(L.vsc_set_stage_a_mode(m))
+        V.frame_stabilize(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[0], ff, fb, V.HyperParams(numIter=3))
+        V.stage_a_fused(of[0], of[1], of[2], pf[0], pf[1], pf[2], pf[0], ff, fb, 6800.0, 6800.0, 2.0, want_adap_in=True)
+    L.vsc_set_stage_a_mode(0)
 torch.cuda.synchronize()
 print("sanitize_driver done,", V.launch_count(), "launches")
