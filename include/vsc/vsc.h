@@ -170,7 +170,8 @@ VSC_API int vsc_stage_a_fused(const float* origPrev, const float* origCur, const
 /* Kernel selection for the fused stage A (vsc_stage_a_fused, vsc_frame_stabilize, the stream object; same results
  * bit for bit).  Low 4 bits: 0 default (= 3 with 128-thread CTAs), 1 = one row per CTA, 2 = a thread walks down a
  * chunk of rows, 3 = + the next row's flow prefetched, 4 = + the next row's loads issued before the current row's
- * arithmetic; bits 4-7 = log2(rows per CTA) (0 = 8, fewer on small frames); | 0x100 = 128-thread CTAs.
+ * arithmetic; bits 4-7 = log2(rows per CTA) or bits 12-19 = rows per CTA (neither: 8, fewer on small frames); | 0x100 =
+ * 128-thread CTAs.
  * vsc_stage_a_fused itself only distinguishes 1 from the rest.  Process-wide; for tests and benchmarks. */
 VSC_API int vsc_set_stage_a_mode(int mode);
 

@@ -47,7 +47,7 @@ def timed(fn, reps=15):
 
 def mode_name(m):
     kind = m & 0xF
-    rows = 1 << ((m >> 4) & 0xF) if (m >> 4) & 0xF else 8
+    rows = (m >> 12) & 0xFF or (1 << ((m >> 4) & 0xF) if (m >> 4) & 0xF else 8)
     s = {0: "default", 1: "row-per-CTA", 2: "walk", 3: "walk+flow-prefetch", 4: "walk+pipelined"}[kind]
     if kind >= 2:
         s += f" rows={rows}" + (" bs=128" if m & 0x100 else "") + ("", " 5cta", " 6cta")[(m >> 9) & 3]
@@ -62,16 +62,17 @@ if FULL:
             MODES.append(kind | (lg << 4))
     MODES += [3 | (2 << 4) | 0x100, 3 | (3 << 4) | 0x100, 4 | (2 << 4) | 0x100, 4 | (3 << 4) | 0x100,
               4 | (4 << 4) | 0x100]
-else:
-    for occ in (0, 0x200, 0x400):
-        for bs in (0, 0x100):
-            for lg in (2, 3, 4):
-                MODES.append(3 | (lg << 4) | bs | occ)
+else:   # (the second sweep, r1_stage_a_walk_events2.txt, also had register-capped builds; those were removed)
+    for bs in (0, 0x100):
+        for lg in (2, 3, 4):
+            MODES.append(3 | (lg << 4) | bs)
+if "--rows" in sys.argv:   # rows per CTA as a number, 128-thread CTAs
+    MODES = [1] + [3 | 0x100 | (r << 12) for r in (3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 20, 24)]
 if NCU:
-    MODES = [1] + [3 | (3 << 4) | bs | occ for occ in (0, 0x200, 0x400) for bs in (0, 0x100)] \
-        + [3 | (4 << 4) | 0x100 | 0x200, 3 | (4 << 4) | 0x100 | 0x400]
+    MODES = [1] + [3 | 0x100 | (r << 12) for r in (4, 5, 6, 7, 8, 9, 10, 12, 16)]
 
-for (W, H) in (() if "--warp" in sys.argv else ((1920, 1080), (3840, 2160))):
+SIZES = ((1280, 720), (1920, 1080), (3840, 2160)) if "--rows" in sys.argv else ((1920, 1080), (3840, 2160))
+for (W, H) in (() if "--warp" in sys.argv else SIZES):
     o8, p8 = synth.frames(W, H, 3)
     of = [V.image_to_gpu(torch.from_numpy(o8[t]).to(dev)) for t in range(3)]
     pf = [V.image_to_gpu(torch.from_numpy(p8[t]).to(dev)) for t in range(3)]
@@ -124,6 +125,8 @@ for (W, H) in (() if "--warp" in sys.argv else ((1920, 1080), (3840, 2160))):
 # r1_warp_variants_*.txt, were removed after these measurements)
 WARP_MODES = [1, 3, 2, 1 | (1 << 4), 1 | (2 << 4)]
 g = torch.Generator(device=dev).manual_seed(0)
+if "--rows" in sys.argv:
+    sys.exit(0)
 if NCU:
     for (C, H, W) in synth.DENSE_4K_WARP[1:]:
         a = torch.randn((1, C, H, W), device=dev, generator=g)

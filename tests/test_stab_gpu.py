@@ -423,7 +423,8 @@ def test_frame_stabilize_fused_equals_unfused(V, dev, W, H, levels, fc):
 
 
 STAGE_A_MODES = [1, 2 | (1 << 4), 2 | (3 << 4), 3 | (1 << 4), 3 | (2 << 4), 3, 3 | (4 << 4), 3 | (3 << 4) | 0x100,
-                 3 | (6 << 4) | 0x100, 4 | (1 << 4), 4 | (2 << 4), 4 | (3 << 4) | 0x100, 4 | (5 << 4)]
+                 3 | (6 << 4) | 0x100, 4 | (1 << 4), 4 | (2 << 4), 4 | (3 << 4) | 0x100, 4 | (5 << 4),
+                 3 | (5 << 12) | 0x100, 3 | (7 << 12), 4 | (3 << 12)]
 
 
 @pytest.mark.parametrize("W,H", [(64, 48), (90, 34), (322, 6), (8, 2), (2, 70), (600, 50)])

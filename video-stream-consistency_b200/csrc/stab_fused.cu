@@ -339,8 +339,14 @@ __global__ void __launch_bounds__(256, 4) stage_a_rows_kernel(StageAPtrs P, int 
 
 // vsc_set_stage_a_mode: low 4 bits = kernel (0 default = 3 with 128-thread CTAs, 1 one row per CTA, 2 row walk,
 // 3 row walk + flow prefetch, 4 row walk + loads one row ahead); bits 4-7 = log2(rows per CTA), 0 = 8 (fewer on
-// small frames); bit 8 = 128-thread CTAs
+// small frames), or bits 12-19 = rows per CTA as a number; bit 8 = 128-thread CTAs
 int g_stage_a_mode = 0;
+// rows per CTA forced by the mode word: bits 12-19 = the number itself, else bits 4-7 = its log2, else 0 (automatic)
+static int stage_a_rows_forced()
+{
+    const int n = (g_stage_a_mode >> 12) & 0xFF, lg = (g_stage_a_mode >> 4) & 0xF;
+    return n ? n : lg ? (1 << lg) : 0;
+}
 
 int launch_stage_a_prep(const float* origPrev, const float* origCur, const float* origNext, const float* procPrev,
     const float* procCur, const float* procNext, const float* lastStab, const float* flowFwd, const float* flowBwd,
@@ -354,8 +360,8 @@ int launch_stage_a_prep(const float* origPrev, const float* origCur, const float
     if (kind >= 2) {
         const bool dflt = (g_stage_a_mode & 0xF) == 0;
         const int bs = (dflt || (g_stage_a_mode & 0x100)) ? 128 : 256;
-        const int lg = (g_stage_a_mode >> 4) & 0xF;
-        int rows = lg ? (1 << lg) : 8;
+        const int lg = stage_a_rows_forced();
+        int rows = lg ? lg : 8;
         // default: 8 rows per CTA unless that leaves fewer than ~4 waves of CTAs (small frames)
         while (!lg && rows > 1 && static_cast<long long>(cdiv(3LL * W, bs)) * cdiv(H, rows) < 4LL * sm_count() * 8)
             rows >>= 1;
@@ -387,8 +393,8 @@ extern "C" int vsc_stage_a_fused(const float* origPrev, const float* origCur, co
         return VSC_E_INVALID;
     // the row-walking kernel uses 32-bit element offsets; one row per CTA otherwise or on request (mode 1)
     if ((g_stage_a_mode & 0xF) != 1 && 3LL * W * H < 0x7fffffffLL) {
-        const int lg = (g_stage_a_mode >> 4) & 0xF;
-        int rows = lg ? (1 << lg) : 8;
+        const int lg = stage_a_rows_forced();
+        int rows = lg ? lg : 8;
         while (!lg && rows > 1 && static_cast<long long>(cdiv(3LL * W, 128)) * cdiv(H, rows) < 4LL * sm_count() * 8)
             rows >>= 1;
         const dim3 grid(cdiv(3LL * W, 128), cdiv(H, rows));
@@ -407,7 +413,7 @@ extern "C" int vsc_stage_a_fused(const float* origPrev, const float* origCur, co
 extern "C" int vsc_set_stage_a_mode(int mode)
 {
     const int kind = mode & 0xF;
-    if (mode < 0 || mode > 0x1FF || kind > 4)
+    if (mode < 0 || mode > 0xFFFFF || (mode & 0xE00) || kind > 4)
         return VSC_E_INVALID;
     vsc::g_stage_a_mode = mode;
     return VSC_OK;
