@@ -70,6 +70,21 @@ def test_argument_validation_without_gpu(V):
     assert L.vsc_stabilizer_push_frame(None, None, None) == -1
 
 
+def test_kernel_selection_words_are_validated(V):
+    """vsc_set_*_mode are plain host-side switches: valid words are accepted and reset, others rejected (no GPU)."""
+    L = V.lib()
+    for ok in (0, 1, 2 | (3 << 4), 3 | (4 << 4) | 0x100, 4 | (2 << 4), 3 | (7 << 12) | 0x100, 3 | (255 << 12)):
+        assert L.vsc_set_stage_a_mode(ok) == 0, hex(ok)
+    for bad in (-1, 5, 0x203, 0x403, 0x803, 1 << 20):
+        assert L.vsc_set_stage_a_mode(bad) == -1, hex(bad)
+    assert L.vsc_set_stage_a_mode(0) == 0
+    for ok in (0, 1, 2, 3, 1 | (1 << 4), 1 | (255 << 4)):
+        assert L.vsc_set_warp_mode(ok) == 0, hex(ok)
+    for bad in (-1, 4, 5, 0x1001):
+        assert L.vsc_set_warp_mode(bad) == -1, hex(bad)
+    assert L.vsc_set_warp_mode(0) == 0
+
+
 def test_workspace_sizes(V):
     L = V.lib()
     n = 1920 * 1080 * 3 * 4
