@@ -41,12 +41,16 @@ void graph_fn(OrtStandinRun& r)
         || out.type != ONNX_TENSOR_ELEMENT_DATA_TYPE_FLOAT || out.shape.size() != 4 || out.shape[3] != 3
         || f1.shape != f2.shape || out.shape[1] != f1.shape[1] || out.shape[2] != f1.shape[2])
         throw Ort::Exception("stand-in graph: unexpected tensor types / shapes");
-    const int H = static_cast<int>(f1.shape[1]), W = static_cast<int>(f1.shape[2]);
-    if (static_cast<size_t>(W) * H > g.px)
-        throw Ort::Exception("stand-in graph: scratch too small");
-    int rc = vsc_rgba8_to_f32x3(static_cast<const uint8_t*>(f1.data), g.a, W, H, r.stream);
-    if (!rc) rc = vsc_rgba8_to_f32x3(static_cast<const uint8_t*>(f2.data), g.b, W, H, r.stream);
-    if (!rc) rc = vsc_warp_hwc3(g.a, g.b, static_cast<float*>(out.data), W, H, 3, r.stream);
+    const int B = static_cast<int>(f1.shape[0]), H = static_cast<int>(f1.shape[1]), W = static_cast<int>(f1.shape[2]);
+    if (static_cast<size_t>(W) * H > g.px || out.shape[0] != f1.shape[0])
+        throw Ort::Exception("stand-in graph: scratch too small / batch mismatch");
+    int rc = 0;
+    for (int n = 0; n < B && !rc; ++n) {   // per sample, like the real graph's batch dimension
+        const size_t px = static_cast<size_t>(W) * H;
+        rc = vsc_rgba8_to_f32x3(static_cast<const uint8_t*>(f1.data) + n * px * 4, g.a, W, H, r.stream);
+        if (!rc) rc = vsc_rgba8_to_f32x3(static_cast<const uint8_t*>(f2.data) + n * px * 4, g.b, W, H, r.stream);
+        if (!rc) rc = vsc_warp_hwc3(g.a, g.b, static_cast<float*>(out.data) + n * px * 3, W, H, 3, r.stream);
+    }
     if (rc)
         throw Ort::Exception(std::string("stand-in graph: ") + vsc_error_string(rc));
 }
@@ -64,7 +68,7 @@ extern "C" {
 
 const char* vsc_fs_test_last_error() { return g_error.c_str(); }
 
-void* vsc_fs_test_create(int W, int H, int netW, int netH, const char* model_path)
+void* vsc_fs_test_create(int W, int H, int netW, int netH, const char* model_path, int batch_directions)
 {
     try {
         OrtStandinGraphs()[kModel] = graph_fn;
@@ -82,7 +86,8 @@ void* vsc_fs_test_create(int W, int H, int netW, int netH, const char* model_pat
         const int rc = vsc_stabilizer_create(&rig->st, W, H, 3);
         if (rc)
             throw std::runtime_error(vsc_error_string(rc));
-        rig->fs = std::make_unique<VscFlowSession>(rig->env, model_path ? model_path : kModel, netW, netH, rig->st);
+        rig->fs = std::make_unique<VscFlowSession>(rig->env, model_path ? model_path : kModel, netW, netH, rig->st, 0,
+            batch_directions != 0);
         return rig.release();
     } catch (const std::exception& e) {
         g_error = e.what();

@@ -156,7 +156,7 @@ def fs():
     lib = C.CDLL(FS_SO)
     lib.vsc_fs_test_last_error.restype = C.c_char_p
     lib.vsc_fs_test_create.restype = C.c_void_p
-    lib.vsc_fs_test_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    lib.vsc_fs_test_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.vsc_fs_test_destroy.argtypes = [C.c_void_p]
     lib.vsc_fs_test_stabilizer.restype = C.c_void_p
     lib.vsc_fs_test_stabilizer.argtypes = [C.c_void_p]
@@ -180,19 +180,21 @@ def test_flow_session_library_exports_the_session_entry_points(fs):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batched", [0, 1], ids=["two-runs", "batch-2"])
 @pytest.mark.parametrize("W,H,scale", [(96, 64, 1), (128, 72, 2), (90, 50, 2)])
-def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale):
+def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale, batched):
     """FlowModel::run + doOneStep through VscFlowSession: frames pushed from host memory once, the network inputs
     written on the device (nearest-neighbour scale for FLOWDOWNSCALE), a persistent IoBinding, enqueue-only runs
     on the stabilizer's stream, flows consumed in place.  The stand-in graph's flow and the stabilized frames must
-    equal the same computation done step by step through the Python binding, bit for bit."""
+    equal the same computation done step by step through the Python binding, bit for bit.  batch-2: both directions
+    of a frame as ONE run on [2,H,W,4] inputs (frame1 = [cur, next], frame2 = [next, cur])."""
     import torch
 
     netW, netH = W // scale, H // scale
     T = 6
     o8, p8 = synth.frames(W, H, T, seed=77)
     before = _fs_counters(fs)
-    rig = fs.vsc_fs_test_create(W, H, netW, netH, None)
+    rig = fs.vsc_fs_test_create(W, H, netW, netH, None, batched)
     assert rig, fs.vsc_fs_test_last_error()
     st = C.c_void_p(fs.vsc_fs_test_stabilizer(rig))
     L = V.lib()
@@ -210,10 +212,14 @@ def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale):
 
         # one direction on its own, copied back: inputs, binding and output slot are the right ones
         got = np.empty((netH, netW, 3), np.float32)
-        assert fs.vsc_fs_test_flow(rig, 1, 2, 0, got.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
-        assert np.array_equal(got, graph(o8[1], o8[2]).cpu().numpy())
-        assert fs.vsc_fs_test_flow(rig, 2, 1, 1, got.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
-        assert np.array_equal(got, graph(o8[2], o8[1]).cpu().numpy())
+        if batched:   # single directions are not available on a batched session
+            assert fs.vsc_fs_test_flow(rig, 1, 2, 0, got.ctypes.data_as(C.c_void_p)) == 1
+            assert b"one batch" in fs.vsc_fs_test_last_error()
+        else:
+            assert fs.vsc_fs_test_flow(rig, 1, 2, 0, got.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
+            assert np.array_equal(got, graph(o8[1], o8[2]).cpu().numpy())
+            assert fs.vsc_fs_test_flow(rig, 2, 1, 1, got.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
+            assert np.array_equal(got, graph(o8[2], o8[1]).cpu().numpy())
 
         for t in range(1, T - 1):
             out = np.zeros((H, W, 4), np.uint8)
@@ -237,8 +243,12 @@ def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale):
     c = _fs_counters(fs)
     steps = T - 2
     assert c["sessions"] - before["sessions"] == 1
-    assert c["bound"] - before["bound"] == 6                        # 2 persistent bindings x 3 tensors, built once
-    assert c["runs"] - before["runs"] == 2 + 2 * steps              # two directions per frame
+    if batched:
+        assert c["bound"] - before["bound"] == 3                    # one persistent binding of [2,H,W,*] tensors
+        assert c["runs"] - before["runs"] == steps                  # ONE run per frame
+    else:
+        assert c["bound"] - before["bound"] == 6                    # 2 persistent bindings x 3 tensors, built once
+        assert c["runs"] - before["runs"] == 2 + 2 * steps          # two directions per frame
     assert c["provider_syncs"] - before["provider_syncs"] == 0      # every Run was enqueue-only
     assert c["saw_domain"] == 1                                     # RegisterCustomOps reached the session options
 
@@ -246,5 +256,5 @@ def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale):
 @pytest.mark.gpu
 def test_flow_session_unknown_model_throws(fs, V, dev):
     """InferenceModelVariant::createSession rethrows ORT's load failure (:175-183); so does the flow session."""
-    assert not fs.vsc_fs_test_create(64, 48, 64, 48, b"models/does-not-exist.onnx")
+    assert not fs.vsc_fs_test_create(64, 48, 64, 48, b"models/does-not-exist.onnx", 0)
     assert b"does-not-exist" in fs.vsc_fs_test_last_error()

@@ -33,8 +33,8 @@ struct VscFlowSession::Binding {
 };
 
 VscFlowSession::VscFlowSession(Ort::Env& env, const std::string& model_path, int netW, int netH,
-    vsc_stabilizer* stabilizer, int device_id)
-    : netW_(netW), netH_(netH), st_(stabilizer)
+    vsc_stabilizer* stabilizer, int device_id, bool batch_directions)
+    : netW_(netW), netH_(netH), batched_(batch_directions), st_(stabilizer)
 {
     if (!stabilizer || netW <= 0 || netH <= 0)
         throw std::runtime_error("VscFlowSession: invalid arguments");
@@ -56,30 +56,40 @@ VscFlowSession::VscFlowSession(Ort::Env& env, const std::string& model_path, int
     session_ = std::make_unique<Ort::Session>(env, model_path.c_str(), options);
 
     // CudaIO's allocations (CudaIO.cpp:37-52), once; zeroed like the reference's
+    const int64_t batch = batched_ ? 2 : 1;
     const size_t frame_bytes = static_cast<size_t>(netW) * netH * 4;
     const size_t flow_bytes = static_cast<size_t>(netW) * netH * 3 * sizeof(float);
     for (int i = 0; i < 2; ++i) {
-        cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&frame_[i]), frame_bytes), "Unable to allocate CUDA memory.");
-        cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&flow_[i]), flow_bytes), "Unable to allocate CUDA memory.");
-        cuda_or_throw(cudaMemset(frame_[i], 0, frame_bytes), "Unable to zero out CUDA memory.");
-        cuda_or_throw(cudaMemset(flow_[i], 0, flow_bytes), "Unable to zero out CUDA memory.");
+        cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&frame_[i]), batch * frame_bytes),
+            "Unable to allocate CUDA memory.");
+        cuda_or_throw(cudaMemset(frame_[i], 0, batch * frame_bytes), "Unable to zero out CUDA memory.");
+    }
+    if (batched_) {   // one [2,H,W,3] output: slot 1 is its second sample
+        cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&flow_[0]), 2 * flow_bytes), "Unable to allocate CUDA memory.");
+        cuda_or_throw(cudaMemset(flow_[0], 0, 2 * flow_bytes), "Unable to zero out CUDA memory.");
+        flow_[1] = flow_[0] + static_cast<size_t>(netW) * netH * 3;
+    } else {
+        for (int i = 0; i < 2; ++i) {
+            cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&flow_[i]), flow_bytes), "Unable to allocate CUDA memory.");
+            cuda_or_throw(cudaMemset(flow_[i], 0, flow_bytes), "Unable to zero out CUDA memory.");
+        }
     }
 
     // runStatic's tensors and binding (:270-313) -- built once instead of per run
     const Ort::MemoryInfo device_memory("Cuda", OrtArenaAllocator, device_id, OrtMemTypeDefault);
-    const int64_t frame_shape[4] = {1, netH, netW, 4};
-    const int64_t flow_shape[4] = {1, netH, netW, 3};
-    for (int slot = 0; slot < 2; ++slot) {
+    const int64_t frame_shape[4] = {batch, netH, netW, 4};
+    const int64_t flow_shape[4] = {batch, netH, netW, 3};
+    for (int slot = 0; slot < (batched_ ? 1 : 2); ++slot) {
         bind_[slot] = std::make_unique<Binding>(*session_);
         Binding& b = *bind_[slot];
         b.values.reserve(3);
         // slot 1 binds the two frame buffers the other way round: the backward run of a frame re-uses the
         // forward run's inputs (flow 2 -> 1 after flow 1 -> 2) without writing them again
-        b.values.push_back(Ort::Value::CreateTensor(device_memory, frame_[slot], frame_bytes, frame_shape, 4,
+        b.values.push_back(Ort::Value::CreateTensor(device_memory, frame_[slot], batch * frame_bytes, frame_shape, 4,
             ONNX_TENSOR_ELEMENT_DATA_TYPE_UINT8));
-        b.values.push_back(Ort::Value::CreateTensor(device_memory, frame_[1 - slot], frame_bytes, frame_shape, 4,
+        b.values.push_back(Ort::Value::CreateTensor(device_memory, frame_[1 - slot], batch * frame_bytes, frame_shape, 4,
             ONNX_TENSOR_ELEMENT_DATA_TYPE_UINT8));
-        b.values.push_back(Ort::Value::CreateTensor(device_memory, flow_[slot], flow_bytes, flow_shape, 4,
+        b.values.push_back(Ort::Value::CreateTensor(device_memory, flow_[slot], batch * flow_bytes, flow_shape, 4,
             ONNX_TENSOR_ELEMENT_DATA_TYPE_FLOAT));
         b.io.BindInput("frame1", b.values[0]);
         b.io.BindInput("frame2", b.values[1]);
@@ -96,14 +106,17 @@ VscFlowSession::~VscFlowSession()
     bind_[0].reset();
     bind_[1].reset();
     session_.reset();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i)
         cudaFree(frame_[i]);
-        cudaFree(flow_[i]);
-    }
+    cudaFree(flow_[0]);
+    if (!batched_)
+        cudaFree(flow_[1]);
 }
 
 const float* VscFlowSession::run(int indexFirst, int indexSecond, int slot)
 {
+    if (batched_)
+        throw std::runtime_error("VscFlowSession::run: the session runs both directions as one batch");
     if (slot < 0 || slot > 1)
         throw std::runtime_error("VscFlowSession::run: slot must be 0 or 1");
     // cpyNImagesToBuffer + QImage::scaled + CudaIO::setData (flowmodel.cpp:126-144) on the device
@@ -115,6 +128,21 @@ const float* VscFlowSession::run(int indexFirst, int indexSecond, int slot)
 
 void VscFlowSession::stabilizeCurrentFrame(uint8_t* out_rgba_host)
 {
+    if (batched_) {
+        // frame1 = [cur, next], frame2 = [next, cur]: sample 0 is the forward pair (:271), sample 1 the backward (:272)
+        const size_t frame_bytes = static_cast<size_t>(netW_) * netH_ * 4;
+        vsc_or_throw(vsc_stabilizer_flow_input(st_, 1, frame_[0], netW_, netH_), "flow input cur");
+        vsc_or_throw(vsc_stabilizer_flow_input(st_, 2, frame_[0] + frame_bytes, netW_, netH_), "flow input next");
+        cudaStream_t stream = static_cast<cudaStream_t>(vsc_stabilizer_compute_stream(st_));
+        cuda_or_throw(cudaMemcpyAsync(frame_[1], frame_[0] + frame_bytes, frame_bytes, cudaMemcpyDeviceToDevice, stream),
+            "Unable to copy data from device to device.");
+        cuda_or_throw(cudaMemcpyAsync(frame_[1] + frame_bytes, frame_[0], frame_bytes, cudaMemcpyDeviceToDevice, stream),
+            "Unable to copy data from device to device.");
+        session_->Run(run_options_, bind_[0]->io);
+        vsc_or_throw(vsc_stabilizer_step_lowres_flow(st_, flow_[0], flow_[1], netW_, netH_, out_rgba_host),
+            "stabilizer step");
+        return;
+    }
     const float* fwd = run(1, 2, 0);                 // videostabilizer.cpp:271
     session_->Run(run_options_, bind_[1]->io);       // :272, run(2, 1): the same two frames, bound swapped
     const float* bwd = flow_[1];

@@ -28,8 +28,13 @@ public:
     // model_path: PWCNet-*-wpreproc.onnx (inputs "frame1","frame2" uint8 [1,netH,netW,4]; output "output" float
     // [1,netH,netW,3], flowmodel.cpp:62-88).  `stabilizer` owns the frames and the compute stream; it must outlive
     // the session.  Throws std::runtime_error / Ort::Exception like InferenceModelVariant::createSession.
+    // batch_directions: stabilizeCurrentFrame() runs the graph ONCE on a batch of two frame pairs -- (cur, next) and
+    // (next, cur) -- instead of twice on one pair: every custom op then sees N = 2 and half the launches disappear
+    // (profiles/time_ops_batched.py: 88 -> 72 us of custom-op GPU time per frame at 1080p/2, 587 -> 515 us for the
+    // dense model at 4K).  The model must accept a batch dimension of 2 (the reference feeds [batchSize, H, W, 4],
+    // flowmodel.cpp:62-70).
     VscFlowSession(Ort::Env& env, const std::string& model_path, int netW, int netH, vsc_stabilizer* stabilizer,
-        int device_id = 0);
+        int device_id = 0, bool batch_directions = false);
     ~VscFlowSession();
     VscFlowSession(const VscFlowSession&) = delete;
     VscFlowSession& operator=(const VscFlowSession&) = delete;
@@ -37,7 +42,8 @@ public:
     // FlowModel::run(frames, results, indexFirst, indexSecond): flow from window frame indexFirst to indexSecond
     // (0 = previous, 1 = current, 2 = next), enqueued on the compute stream; the result lands in output slot
     // `slot` (0 or 1: forward / backward, so that both directions of a frame can be pending).  Returns the device
-    // pointer of the [netH, netW, 3] float flow; valid until the next run into the same slot.
+    // pointer of the [netH, netW, 3] float flow; valid until the next run into the same slot.  Not available on a
+    // session created with batch_directions (throws).
     const float* run(int indexFirst, int indexSecond, int slot);
 
     // retrieveOpticalFlow + doOneStep (videostabilizer.cpp:167-279): both directions, then the stabilization step
@@ -50,9 +56,10 @@ public:
 private:
     struct Binding;
     int netW_, netH_;
+    bool batched_;
     vsc_stabilizer* st_;
-    uint8_t* frame_[2] = {nullptr, nullptr};   // bound inputs
-    float* flow_[2] = {nullptr, nullptr};      // bound outputs, one per slot
+    uint8_t* frame_[2] = {nullptr, nullptr};   // bound inputs ([1,H,W,4] each; batched: [2,H,W,4] each)
+    float* flow_[2] = {nullptr, nullptr};      // bound outputs, one per slot (batched: flow_[1] = flow_[0] + H*W*3)
     std::unique_ptr<Ort::Session> session_;
     std::unique_ptr<Binding> bind_[2];         // one persistent IoBinding per output slot
     Ort::RunOptions run_options_;
