@@ -195,27 +195,95 @@ def stream_frame_index(t):
     return (t - 1) % NFRAMES, t % NFRAMES, (t + 1) % NFRAMES
 
 
+# ------------------------------------------------------------------------------------------------ config
+def job_config(workload, world):
+    """the `config` object of the JSON line -- built by BOTH arms from the same arguments, so that the two lines
+    describe the same job key for key"""
+    wl = WORKLOADS[workload]
+    W, H, fw, fh = wl["W"], wl["H"], wl["flowW"], wl["flowH"]
+    return {"workload": workload + ": " + wl["desc"], "resolution": f"{W}x{H}", "flow_resolution": f"{fw}x{fh}",
+            "numIter": 150, "pyramidLevels": 2, "streams": world,
+            "parallelism": f"replicas x{world} (independent video streams, no collective)",
+            "l2": (f"inputs larger than L2: {NFRAMES} frame pairs cycled, per-step working set "
+                   f"{(12 * 4 + 6 * 4) * W * H / 1e6:.0f} MB of solver state > 126 MB L2" if W * H * 72 > 126e6
+                   else f"{NFRAMES} frame pairs cycled; solver state {72 * W * H / 1e6:.0f} MB per sweep"),
+            "custom_op_bytes_per_step": op_bytes(wl),
+            "out_of_scope": "PWC-Net convolutions (ORT graph): synthetic device-resident activations"}
+
+
+# ------------------------------------------------------------------------------------------------ host placement
+def bind_near_gpu(local_rank):
+    """Pin this process to the CPU cores of the GPU's NUMA node BEFORE any pinned buffer is allocated.
+
+    torchrun starts every rank with the same affinity mask; pinned staging memory is then first-touched on whatever
+    node the rank happens to run on, and the per-frame 25 MB (1080p) of H2D + D2H of ranks whose GPU hangs off the
+    other socket crosses the inter-socket link.  Binding by GPU locality keeps every stream's host traffic local.
+    Returns a short description for the JSON line; never fails (a restricted cpuset just keeps the old mask)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            tok = vis.split(",")[local_rank].strip()
+            h = pynvml.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(tok))
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:      # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if not want:
+            return {"numa_node": node, "bound": False, "why": "GPU-local cores are outside this process's cpuset",
+                    "allowed": len(allowed)}
+        os.sched_setaffinity(0, want)
+        return {"numa_node": node, "bound": True, "cores": len(want)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
-def bench_ours(args, rank, world):
+_frames_cache = {}
+
+
+def host_frames_cached(W, H):
+    if (W, H) not in _frames_cache:
+        _frames_cache.clear()            # one resolution at a time (pinned 4K sets are 0.5 GB)
+        _frames_cache[(W, H)] = make_host_frames(W, H, pin=True)
+    return _frames_cache[(W, H)]
+
+
+def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_clocks=True):
+    """one workload on this rank's GPU: device-resident arm, end-to-end arm, kernel rooflines.
+    -> dict of per-rank raw numbers (times not yet reduced over ranks)"""
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     import synth
     import vsc_b200 as V
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
+    local = dev.index
+    wl = WORKLOADS[name]
     W, H, fw, fh = wl["W"], wl["H"], wl["flowW"], wl["flowH"]
-    K, Wm = args.steps, args.warmup
     peaks, peak_src = measured_peaks()
-
-    ho, hp = make_host_frames(W, H, pin=True)
+    ho, hp = host_frames_cached(W, H)
     files = bool(wl.get("files"))
     flow_c = 2 if files else 3    # .flo files hold (u, v) pairs
     flf, flb = synth.flows(fw, fh, flow_c)
@@ -235,8 +303,6 @@ def bench_ours(args, rank, world):
     lowres = (fw, fh) != (W, H)
     upf = torch.empty((H, W, 3), device=dev) if lowres else d_flf
     upb = torch.empty((H, W, 3), device=dev) if lowres else d_flb
-    import ctypes as C
-
     L = V.lib()
 
     def dptr(t):
@@ -272,9 +338,10 @@ def bench_ours(args, rank, world):
         gpu_id = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
     except Exception:
         gpu_id = str(local)
-    clocks = ClockSampler(gpu_id)
-    clocks.start()
-    time.sleep(0.25)
+    clocks = ClockSampler(gpu_id) if sample_clocks else None
+    if clocks:
+        clocks.start()
+        time.sleep(0.25)
     n0 = V.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
@@ -283,7 +350,6 @@ def bench_ours(args, rank, world):
         step_resident(1 + Wm + t)
     e1.record()
     barrier()
-    t_host1 = time.perf_counter()
     launches = V.launch_count() - n0
     ms_res = e0.elapsed_time(e1)
 
@@ -338,14 +404,59 @@ def bench_ours(args, rank, world):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     ms_e2e = (t1 - t0) * 1e3
-    clk = clocks.stop(t_host0, t1)
+    clk = clocks.stop(t_host0, t1) if clocks else None
+
+    # pinned-copy bandwidth of this rank's host<->GPU path, alone (explains e2e when ranks share a root complex)
+    probe = torch.empty((H, W, 4), device=dev, dtype=torch.uint8)
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe.copy_(ho[0], non_blocking=True)
+    torch.cuda.synchronize()
+    ea.record()
+    for i in range(4):
+        probe.copy_(ho[i % NFRAMES], non_blocking=True)
+    eb.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * W * H * 4 / (ea.elapsed_time(eb) * 1e-3) / 1e9
+    del probe
+
+    # ---------------- sustained: seconds of back-to-back frames (SM clock settles below boost) ----------------
+    sustained = None
+    if sustained_s > 0:
+        sclk = ClockSampler(gpu_id)
+        sclk.start()
+        time.sleep(0.2)
+        chunk = max(8, int(0.25 / max(ms_res / K * 1e-3, 1e-5)))
+        evs = [torch.cuda.Event(enable_timing=True)]
+        ts0 = time.perf_counter()
+        evs[0].record()
+        frames_done, t = 0, 1 + Wm + K
+        while True:
+            for _ in range(chunk):
+                step_resident(t)
+                t += 1
+            frames_done += chunk
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            evs.append(ev)
+            ev.synchronize()
+            if evs[0].elapsed_time(ev) >= sustained_s * 1e3:
+                break
+        ts1 = time.perf_counter()
+        total_ms = evs[0].elapsed_time(evs[-1])
+        last_ms = evs[-2].elapsed_time(evs[-1])
+        c = sclk.stop(ts0, ts1)
+        sustained = {"seconds": total_ms * 1e-3, "frames": frames_done, "value": frames_done / (total_ms * 1e-3),
+                     "unit": "frames/s", "last_chunk_value": chunk / (last_ms * 1e-3),
+                     "sm_mhz_median": c["sm_mhz"], "sm_max_mhz": c["sm_max_mhz"], "clock_samples": c.get("samples"),
+                     "reasons": c["reasons"],
+                     "note": "device-resident arm run back to back for this long on rank 0's GPU; CUDA events"}
     st.close()
     if flow_dir:
         shutil.rmtree(flow_dir, ignore_errors=True)
 
     # ---------------- roofline of the dominant kernel: the level-0 solver ----------------
     # marginal time of n sweeps = t(2n) - t(n), CUDA events on the launching stream.  In the default mode the
-    # sweeps run as temporally blocked passes (solver_stream_kernel<8>, 8 sweeps per launch); the unblocked
+    # sweeps run as temporally blocked passes (solver_stream_kernel<T>, T sweeps per launch); the unblocked
     # sweep kernel is timed beside it (mode 1).  Algorithmic bytes: 72 B/pixel/sweep.
     def time_solve(iters):
         x = d_p[1].clone()
@@ -373,10 +484,12 @@ def bench_ours(args, rank, world):
     alg_bytes = T_main * 72.0 * W * H
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
     unblocked = 72.0 * W * H / (sweep_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(f"solver_stream{T_main}_dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get(name, {}).get(f"solver_stream{T_main}_dram_bytes_per_launch")
+        traffic_src = tj.get("_source")
     except Exception:
         pass
 
@@ -404,50 +517,124 @@ def bench_ours(args, rank, world):
     stage_a_ms = ea.elapsed_time(eb) / 16
     stage_a_bytes = (84.0 + 24.0 + 4.0 * 2 * flow_c) * W * H   # 7 images read, 2 written, 2 flows of flow_c channels
     stage_a_gbs = stage_a_bytes / (stage_a_ms * 1e-3) / 1e9
-    del f_full, sa_out
+
+    # the custom ops at the two largest level shapes of this workload, each timed alone (CUDA events, 20 launches
+    # over two independent tensor sets): Warp 4(2C+2)HW bytes, Correlation 4(2C+81)HW bytes
+    ops_roof = []
+    if wl["corr"]:
+        def time_op(fn, reps=20):
+            for _ in range(3):
+                fn(0)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                fn(i & 1)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        for li in sorted(range(len(wl["warp"])), key=lambda i: -wl["warp"][i][1] * wl["warp"][i][2])[:2]:
+            Cc, h, w = wl["warp"][li]
+            ms = time_op(lambda d: V.warp(sets[d][1][li][0], sets[d][1][li][1], out=sets[d][1][li][2]))
+            nb = 4.0 * h * w * (2 * Cc + 2)
+            ops_roof.append({"kernel": "custom::Warp", "shape": [Cc, h, w], "us_per_launch": ms * 1e3,
+                             "achieved": nb / (ms * 1e-3) / 1e9, "frac": nb / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "algorithmic_bytes_per_launch": nb})
+        for li in sorted(range(len(wl["corr"])), key=lambda i: -wl["corr"][i][1] * wl["corr"][i][2])[:2]:
+            Cc, h, w = wl["corr"][li]
+            ms = time_op(lambda d: V.correlation(sets[d][0][li][0], sets[d][0][li][1], out=sets[d][0][li][2]))
+            nb = 4.0 * h * w * (2 * Cc + 81)
+            ops_roof.append({"kernel": "custom::Correlation", "shape": [Cc, h, w], "us_per_launch": ms * 1e3,
+                             "achieved": nb / (ms * 1e-3) / 1e9, "frac": nb / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "algorithmic_bytes_per_launch": nb,
+                             "gflops": 2.0 * 81 * Cc * h * w / (ms * 1e-3) / 1e9})
+
+    dram_frac = (traffic / (pass_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None
+    roofline = {"kernel": f"solver_stream_kernel<{T_main}> (level 0, {T_main} Jacobi sweeps per launch, on-chip)",
+                # what limits the kernel per ncu (profiles/): instruction issue + shared-memory wavefronts; the HBM
+                # roofline in ALGORITHMIC bytes is kept as the contract's yardstick, dram_frac is the real DRAM load
+                "bound": "issue/smem", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "dram_frac": dram_frac,
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": pass_ms * 1e3,
+                "hbm_floor_us": (traffic / (peaks["hbm_gbs"] * 1e9) * 1e6) if traffic else None,
+                "peak_source": peak_src,
+                "note": f"algorithmic bytes = {T_main} sweeps x 72 B/pixel; temporal blocking keeps "
+                        f"{T_main - 1} of {T_main} sweeps on chip, so `frac` may exceed 1; `dram_frac` = ncu DRAM "
+                        "bytes per launch / launch time / HBM peak is the fraction of HBM bandwidth actually used",
+                "unblocked_sweep": {"kernel": "solver_sweep_vec_kernel", "bound": "hbm", "achieved": unblocked,
+                                    "frac": unblocked / peaks["hbm_gbs"], "us_per_launch": sweep_ms * 1e3},
+                "fused_stage_a": {"kernel": "stage_a_rows_kernel (warp x5 -> adaptive blend -> weight, one pass)",
+                                  "bound": "hbm", "achieved": stage_a_gbs, "frac": stage_a_gbs / peaks["hbm_gbs"],
+                                  "us_per_launch": stage_a_ms * 1e3, "algorithmic_bytes_per_launch": stage_a_bytes},
+                "custom_ops": ops_roof}
+    e2e = {"h2d_bytes_per_step": 2 * W * H * 4 + (2 * fw * fh * 8 if files else 0),
+           "file_bytes_per_step": 2 * (12 + fw * fh * 8) if files else 0, "d2h_bytes_per_step": W * H * 4,
+           "timing": "host clock between full device synchronisations"}
+    del d_o, d_p, last, cons, ws, sets, f_full, sa_out, out8, outs
+    torch.cuda.empty_cache()
+    return dict(ms_res=ms_res, ms_e2e=ms_e2e, launches=launches, clocks=clk, roofline=roofline, e2e=e2e,
+                sustained=sustained, h2d_gbs=h2d_gbs)
+
+
+def bench_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    placement = bind_near_gpu(local) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    r = run_workload(args, args.workload, K, Wm, rank, world, dev,
+                     sustained_s=args.sustained if (rank == 0 and world == 1) else 0.0)
 
     # ---------------- aggregate over ranks (max time) ----------------
-    (ms_res, ms_e2e), (launches,) = reduce_over_ranks([ms_res, ms_e2e], [launches], world, dev)
+    (ms_res, ms_e2e, neg_h2d), (launches, nbound) = reduce_over_ranks(
+        [r["ms_res"], r["ms_e2e"], -r["h2d_gbs"]], [r["launches"], int(bool(placement.get("bound")))], world, dev)
 
     result = None
     if rank == 0:
+        wl = WORKLOADS[args.workload]
         cpu = cpu_baseline(wl, args) if world == 1 and not args.no_cpu_baseline else None
         result = {
             "metric": "stabilized_frames_per_sec", "value": aggregate_fps(world, K, ms_res), "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_res / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "resolution": f"{W}x{H}",
-                       "flow_resolution": f"{fw}x{fh}", "numIter": hpar.numIter, "pyramidLevels": hpar.pyramidLevels,
-                       "streams": world, "parallelism": f"replicas x{world} (independent video streams, no collective)",
-                       "l2": f"inputs larger than L2: {NFRAMES} frame pairs cycled, per-step working set "
-                             f"{(12 * 4 + 6 * 4) * W * H / 1e6:.0f} MB of solver state > 126 MB L2" if W * H * 72 > 126e6
-                       else f"{NFRAMES} frame pairs cycled; solver state {72 * W * H / 1e6:.0f} MB per sweep",
-                       "custom_op_bytes_per_step": op_bytes(wl),
-                       "out_of_scope": "PWC-Net convolutions (ORT graph): synthetic device-resident activations"},
-            "e2e": {"value": aggregate_fps(world, K, ms_e2e), "unit": "frames/s",
-                    "h2d_bytes_per_step": 2 * W * H * 4 + (2 * fw * fh * 8 if files else 0),
-                    "file_bytes_per_step": 2 * (12 + fw * fh * 8) if files else 0,
-                    "d2h_bytes_per_step": W * H * 4, "timing": "host clock between full device synchronisations",
-                    "ms_per_step": ms_e2e / K},
+            "config": job_config(args.workload, world),
+            "e2e": dict(value=aggregate_fps(world, K, ms_e2e), unit="frames/s", ms_per_step=ms_e2e / K,
+                        pinned_h2d_gbs_min_over_ranks=-neg_h2d, host_placement=placement,
+                        ranks_bound_to_gpu_numa_node=nbound, **r["e2e"]),
             "gpu_launches": int(launches),
-            "clocks": clk,
-            "roofline": {"kernel": f"solver_stream_kernel<{T_main}> (level 0, {T_main} Jacobi sweeps per launch, on-chip)",
-                         "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                         "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": pass_ms * 1e3,
-                         "peak_source": peak_src,
-                         "note": f"algorithmic bytes = {T_main} sweeps x 72 B/pixel; temporal blocking keeps "
-                                 f"{T_main - 1} of {T_main} sweeps on chip, so achieved may exceed the HBM peak (see "
-                                 "traffic for DRAM bytes)",
-                         "unblocked_sweep": {"kernel": "solver_sweep_vec_kernel", "achieved": unblocked,
-                                             "frac": unblocked / peaks["hbm_gbs"], "us_per_launch": sweep_ms * 1e3},
-                         "fused_stage_a": {"kernel": "stage_a_rows_kernel (warp x5 -> adaptive blend -> weight, one pass)",
-                                           "achieved": stage_a_gbs, "frac": stage_a_gbs / peaks["hbm_gbs"],
-                                           "us_per_launch": stage_a_ms * 1e3,
-                                           "algorithmic_bytes_per_launch": stage_a_bytes}},
+            "clocks": r["clocks"],
+            "roofline": r["roofline"],
         }
+        if r["sustained"]:
+            result["sustained"] = r["sustained"]
         if cpu:
             result["cpu_baseline"] = cpu
+    # ---------------- the other single-GPU BASELINE configs, short runs (N = 1 only) ----------------
+    if world == 1 and not args.no_extras and args.workload == "1080p-light":
+        extras = []
+        for name in ("4k-stab", "4k-dense"):
+            Ke = max(6, min(K, 12))
+            x = run_workload(args, name, Ke, 3, rank, world, dev, sample_clocks=True)
+            wlx = WORKLOADS[name]
+            rec = {"workload": name, "config": job_config(name, 1), "steps": Ke, "warmup": 3,
+                   "value": aggregate_fps(1, Ke, x["ms_res"]), "unit": "frames/s", "ms_per_step": x["ms_res"] / Ke,
+                   "e2e": dict(value=aggregate_fps(1, Ke, x["ms_e2e"]), unit="frames/s", **x["e2e"]),
+                   "gpu_launches": int(x["launches"]), "clocks": x["clocks"],
+                   "roofline": {k: x["roofline"][k] for k in ("kernel", "bound", "achieved", "frac", "traffic", "dram_frac",
+                                                              "us_per_launch", "fused_stage_a", "unblocked_sweep",
+                                                              "custom_ops")}}
+            if not args.no_cpu_baseline:
+                rec["cpu_baseline"] = cpu_baseline(wlx, args, frames=2, band_h=wlx["H"] // 8)
+            extras.append(rec)
+        result["extra"] = extras
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -550,8 +737,7 @@ def bench_reference(args, rank, world):
         "impl": "reference", "metric": "stabilized_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dt / K * 1e3 / (band_h / H),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + wl["desc"], "resolution": f"{wl['W']}x{H}",
-                   "numIter": 150, "pyramidLevels": 2},
+        "config": job_config(args.workload, world),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -566,6 +752,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-light", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short 4k-stab / 4k-dense runs (N = 1 only)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="keep the launcher's CPU affinity")
+    ap.add_argument("--sustained", type=float, default=3.0,
+                    help="seconds of back-to-back device-resident frames for the `sustained` record (N = 1; 0 = off)")
     ap.add_argument("--solver-mode", type=lambda x: int(x, 0), default=0, help="vsc_set_solver_mode value (A/B runs)")
     ap.add_argument("--stage-a-mode", type=lambda x: int(x, 0), default=0, help="vsc_set_stage_a_mode value (A/B runs)")
     args = ap.parse_args()

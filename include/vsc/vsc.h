@@ -225,11 +225,22 @@ VSC_API vsc_hyper_params* vsc_stabilizer_hyper_params(vsc_stabilizer* s);
  * window (upload + u8->f32 on the copy stream).  The third push after creation/reset also
  * initialises lastStabilizedFrame from that processed frame (preloadProcessedFrames :152).
  * Host buffers may be pageable (staged through internal pinned buffers) or pinned
- * (vsc_host_alloc / cudaHostRegister: copied directly); they may be reused once the call returns
- * if pageable, or after the next vsc_stabilizer_step/sync if pinned. */
+ * (vsc_host_alloc / cudaHostRegister: copied directly).  A pageable buffer may be reused as soon as the
+ * call returns.  A PINNED buffer is read by an asynchronous copy that may still be pending when this call --
+ * and any following vsc_stabilizer_step -- has returned: it may be overwritten only after
+ * vsc_stabilizer_sync (or vsc_stabilizer_wait_uploads, which waits for the uploads alone).  The same holds
+ * for pinned flows of vsc_stabilizer_step_host_flow, and a pinned out_rgba_host is complete only after
+ * vsc_stabilizer_sync. */
 VSC_API int vsc_stabilizer_push_frame(vsc_stabilizer* s, const uint8_t* orig_rgba_host,
     const uint8_t* proc_rgba_host);
-/* doOneStep(): stabilise window[1] with flow cur->next (flowFwd) and the flow the reference uses
+/* Stream contract of every *_dev argument of the vsc_stabilizer_* calls: the call enqueues work on the object's
+ * own compute stream (vsc_stabilizer_compute_stream, created cudaStreamNonBlocking) and returns at once.  The
+ * caller must (a) make that stream wait for whatever stream produced a *_dev input (cudaEventRecord on the
+ * producer + cudaStreamWaitEvent on the compute stream) BEFORE the call, (b) keep the memory alive and unmodified
+ * until the step has run (vsc_stabilizer_sync, or an event recorded on the compute stream after the call), and
+ * (c) order any consumer of a *_dev output after the compute stream in the same way.
+ *
+ * doOneStep(): stabilise window[1] with flow cur->next (flowFwd) and the flow the reference uses
  * as cur->prev (flowBwd), both DEVICE HWC images of flow_channels channels at frame resolution.
  * Writes the RGBA8888 result to out_rgba_host (if non-NULL; valid after vsc_stabilizer_sync),
  * updates lastStabilizedFrame and pops the window front.  Requires 3 frames in the window. */
@@ -261,6 +272,10 @@ VSC_API int vsc_stabilizer_prefetch_flow_files(vsc_stabilizer* s, const char* fl
  * the compute stream; requires 3 frames in the window. */
 VSC_API int vsc_stabilizer_flow_input(vsc_stabilizer* s, int window_index, uint8_t* dst_dev, int netW, int netH);
 VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
+/* blocks until every host->device copy enqueued so far (frames of vsc_stabilizer_push_frame, flows of
+ * vsc_stabilizer_step_host_flow) has left its source buffer: after it, pinned input buffers may be overwritten.
+ * Does not wait for any kernel. */
+VSC_API int vsc_stabilizer_wait_uploads(vsc_stabilizer* s);
 /* device pointer to the fp32 result of the last step (W*H*3 floats), for tests */
 VSC_API const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s);
 /* enqueue a device-to-device copy of that result into dst_dev on the compute stream */

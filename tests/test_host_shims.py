@@ -113,9 +113,11 @@ def test_ort_warp_through_registration(ort, O, dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("W,H", [(64, 48), (45, 37)])
+@pytest.mark.parametrize("W,H", [(64, 48), (45, 37), (1920, 1080), (3840, 2160)])
 def test_stabilization_shim_sequence(O, dev, W, H):
-    """GPUImage + flowconsistency.cuh drop-in: preload + 2 doOneStep calls from RGBA host frames vs the oracle."""
+    """GPUImage + flowconsistency.cuh drop-in: preload + 2 doOneStep calls from RGBA host frames vs the oracle.
+    At 1080p / 4K the D2D copyFrom calls take tens of microseconds: a get_* kernel that were not ordered behind
+    them (copies on the legacy stream, kernels on a non-blocking stream) would read half-copied images."""
     if not os.path.exists(STAB_SO):
         pytest.skip("stabilization shim test library not built (needs the reference headers at build time)")
     lib = C.CDLL(STAB_SO)
@@ -129,7 +131,8 @@ def test_stabilization_shim_sequence(O, dev, W, H):
     of = [O.rgba8_to_f32x3(x) for x in o8]
     pf = [O.rgba8_to_f32x3(x) for x in p8]
     last = pf[2]
-    for t in (1, 2):
+    O.use_all_cores()
+    for t in (1, 2) if W < 3840 else (1,):
         rgba = np.zeros((H, W, 4), np.uint8)
         cons = np.zeros((H, W, 3), np.float32)
         rc = lib.vsc_shim_step(h, ff.ctypes.data_as(F32P), fb.ctypes.data_as(F32P), C.c_float(6800.0),
@@ -140,7 +143,7 @@ def test_stabilization_shim_sequence(O, dev, W, H):
         last = ref_f
         assert np.abs(cons - ref_f).max() <= 3e-5
         assert np.abs(rgba.astype(np.int32) - ref8.astype(np.int32)).max() <= 1
-        if t == 1:
+        if t == 1 and W < 3840:
             assert lib.vsc_shim_push(h, o8[3].ctypes.data_as(C.c_void_p), p8[3].ctypes.data_as(C.c_void_p)) == 0
     lib.vsc_shim_destroy(h)
 

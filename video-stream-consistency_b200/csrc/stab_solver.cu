@@ -20,7 +20,7 @@
 //     i.e. 2 state images (out, u) + 2 coefficient images = 72 B/pixel/sweep unblocked, 7 flops;
 //   * 128-bit accesses over the flattened row of 3W floats (x-neighbours are +-3 floats away).
 // The sweep arithmetic uses explicit FMAs; it is mathematically the reference's update and
-// differs from it only in fp32 rounding (parity: tests/test_solver.py, tolerance stated there).
+// differs from it only in fp32 rounding (parity: tests/test_stab_gpu.py -- test_solver_vs_jacobi_oracle, test_sequence_vs_reference_gpu_fixtures; tolerances stated there).
 #include "vsc_common.cuh"
 
 namespace vsc {

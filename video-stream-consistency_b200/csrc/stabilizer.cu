@@ -568,6 +568,20 @@ extern "C" int vsc_stabilizer_sync(vsc_stabilizer* s)
     return rc;
 }
 
+extern "C" int vsc_stabilizer_wait_uploads(vsc_stabilizer* s)
+{
+    if (!s)
+        return VSC_E_INVALID;
+    // every H2D goes through the copy stream; the events below are recorded right behind the copies
+    int rc = VSC_OK;
+    for (int k = 0; k < kSlots && !rc; ++k)
+        if (s->slot_used[k])
+            rc = cu(cudaEventSynchronize(s->slot_h2d[k]));
+    if (!rc && s->flow_used)
+        rc = cu(cudaEventSynchronize(s->flow_ready));
+    return rc;
+}
+
 extern "C" const float* vsc_stabilizer_last_output_dev(vsc_stabilizer* s) { return s ? s->lastStab : nullptr; }
 
 extern "C" int vsc_stabilizer_copy_last_output(vsc_stabilizer* s, float* dst_dev)

@@ -10,6 +10,11 @@
 // (here: enqueue on one private stream, then cudaStreamSynchronize); CUDA errors print and
 // exit(1) like checkError (flowconsistency.cu:25-31); GPUImage keeps its public fields, deep-copy
 // constructor and the six copy* methods with the reference's messages and exceptions.
+// Ordering: the reference ran every kernel and every cudaMemcpy on the legacy default stream, so a
+// D2D copyFrom followed by a get_* call was ordered implicitly.  Here the kernels run on a private
+// non-blocking stream, which never orders itself against the legacy stream, and a D2D cudaMemcpy does not
+// block the host -- so every GPUImage copy* method is issued on the SAME private stream and then
+// synchronised: copyFrom -> get_* -> copyFrom sequences of the unmodified host code stay ordered.
 // What changes underneath: no per-call cudaMalloc/cudaFree (get_consist_out's scratch and the
 // RGBA staging buffers are cached and only ever grow), no cudaDeviceSynchronize, sm_100a kernels.
 #include "flowconsistency.cuh"
@@ -86,6 +91,16 @@ void finish(int rc, const char* stage)
                   << (rc < 0 ? vsc_error_string(rc) : cudaGetErrorString(e)) << std::endl;
         std::exit(1);
     }
+}
+
+// a cudaMemcpy of the reference, on the shim's stream (see "Ordering" above); false on failure
+bool copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
+{
+    std::lock_guard<std::mutex> lock(shim().mu);
+    cudaStream_t st = shim().s();
+    if (cudaMemcpyAsync(dst, src, bytes, kind, st) != cudaSuccess)
+        return false;
+    return cudaStreamSynchronize(st) == cudaSuccess;
 }
 
 }  // namespace
@@ -165,7 +180,7 @@ void GPUImage::copyFrom(const GPUImage& other)
 {
     if (other.width == width && other.height == height && other.channels == channels) {
         const size_t nelems = static_cast<size_t>(width) * height * channels;
-        if (cudaMemcpy(data, other.data, nelems * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess)
+        if (!copy_sync(data, other.data, nelems * sizeof(float), cudaMemcpyDeviceToDevice))
             throw std::runtime_error("Unable to copy data from device to device.");
     } else {
         std::cerr << "Invalid dimensions" << std::endl;
@@ -176,7 +191,7 @@ void GPUImage::copyFrom(const std::vector<float>& vec)
 {
     const size_t nelems = static_cast<size_t>(width) * height * channels;
     if (nelems == vec.size()) {
-        if (cudaMemcpy(data, vec.data(), nelems * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        if (!copy_sync(data, vec.data(), nelems * sizeof(float), cudaMemcpyHostToDevice))
             throw std::runtime_error("Unable to copy data from device to host.");
     } else {
         std::cerr << "Invalid dimensions" << std::endl;
@@ -187,7 +202,7 @@ void GPUImage::copyFrom(const std::vector<std::byte>& vec)
 {
     const size_t nelems = static_cast<size_t>(width) * height * channels;
     if (nelems * sizeof(float) == vec.size())
-        cudaMemcpy(data, vec.data(), nelems * sizeof(float), cudaMemcpyHostToDevice);
+        (void)copy_sync(data, vec.data(), nelems * sizeof(float), cudaMemcpyHostToDevice);
     else
         throw std::runtime_error("Invalid dimensions. Length of byte-array differs from expected number of floats");
 }
@@ -196,7 +211,7 @@ void GPUImage::copyFromCudaBuffer(const void* resourcePointer, size_t byteSize)
 {
     const size_t nelems = static_cast<size_t>(width) * height * channels;
     if (nelems * sizeof(float) == byteSize) {
-        if (cudaMemcpy(data, resourcePointer, byteSize, cudaMemcpyDeviceToDevice) != cudaSuccess)
+        if (!copy_sync(data, resourcePointer, byteSize, cudaMemcpyDeviceToDevice))
             throw std::runtime_error("Unable to copy data from device to host.");
     } else {
         throw std::runtime_error("Invalid dimensions. Length of byte-array differs from expected number of floats");

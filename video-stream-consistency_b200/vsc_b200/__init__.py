@@ -248,7 +248,29 @@ class Stabilizer:
         self.W, self.H, self.flow_channels = int(width), int(height), int(flow_channels)
         self._h = C.c_void_p(0)
         check(lib().vsc_stabilizer_create(C.byref(self._h), self.W, self.H, self.flow_channels))
-        self._keep = []
+        self._inflight = []     # tensors / host buffers the asynchronous steps still use (released by sync())
+        self._xstream = None
+
+    # The pipeline object runs on its own non-blocking compute stream.  Device tensors handed to it were produced
+    # on torch's current stream, and tensors it fills are consumed there: order the two with events, and keep
+    # every buffer of an enqueued step referenced until the next sync() so that torch's caching allocator (or the
+    # garbage collector, for host arrays) cannot recycle memory the stream still uses.
+    def _compute_ext(self):
+        if self._xstream is None:
+            self._xstream = torch.cuda.ExternalStream(self.compute_stream)
+        return self._xstream
+
+    def _hold(self, *bufs):
+        self._inflight.append(bufs)
+        if len(self._inflight) > 64:        # a caller that never syncs: calls that far back are long done
+            del self._inflight[:32]
+
+    def _after_torch(self, *bufs):
+        self._compute_ext().wait_stream(torch.cuda.current_stream())
+        self._hold(*bufs)
+
+    def _before_torch(self):
+        torch.cuda.current_stream().wait_stream(self._compute_ext())
 
     def close(self):
         if getattr(self, "_h", None) and lib is not None:   # `lib` is None while the interpreter shuts down
@@ -275,7 +297,7 @@ class Stabilizer:
 
     def push_frame(self, orig_rgba_host, proc_rgba_host):
         """loadFrame: host RGBA8888 [H,W,4] x2 (pinned tensors are copied without staging)."""
-        self._keep = [orig_rgba_host, proc_rgba_host]
+        self._hold(orig_rgba_host, proc_rgba_host)   # pinned frames are read asynchronously
         check(lib().vsc_stabilizer_push_frame(self._h, self._host_u8(orig_rgba_host, "orig"),
                                               self._host_u8(proc_rgba_host, "proc")))
 
@@ -283,6 +305,7 @@ class Stabilizer:
         """doOneStep.  Flows: device HWC at frame resolution, or lower (FLOWDOWNSCALE) -> upsampled inside."""
         fh, fw = int(flowFwd.shape[0]), int(flowFwd.shape[1])
         outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
+        self._after_torch(flowFwd, flowBwd, out_rgba_host)
         if (fw, fh) == (self.W, self.H):
             check(lib().vsc_stabilizer_step(self._h, _f32(flowFwd, "flowFwd"), _f32(flowBwd, "flowBwd"), outp))
         else:
@@ -306,7 +329,7 @@ class Stabilizer:
         pb, bw, bh, bc = fptr(flowBwd_host, "flowBwd")
         if (fw, fh, fc) != (bw, bh, bc) or fc != self.flow_channels:
             raise VscError("step_host_flow: flows must have the same shape and the stabilizer's channel count")
-        self._keep_flow = [flowFwd_host, flowBwd_host]
+        self._hold(flowFwd_host, flowBwd_host, out_rgba_host)
         outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
         check(lib().vsc_stabilizer_step_host_flow(self._h, pf, pb, fw, fh, outp))
 
@@ -314,6 +337,7 @@ class Stabilizer:
         """doOneStep of the file mode (-f <flowdir>): reads <flow_dir>/frame_%06d.flo (current_frame + 1) and
         frame_%06d_bwd.flo (current_frame) like FileStabilizer::retrieveOpticalFlow, then steps."""
         outp = self._host_u8(out_rgba_host, "out") if out_rgba_host is not None else C.c_void_p(0)
+        self._hold(out_rgba_host)
         check(lib().vsc_stabilizer_step_flow_files(self._h, os.fsencode(flow_dir), int(current_frame), outp),
               os.fspath(flow_dir))
 
@@ -323,7 +347,9 @@ class Stabilizer:
         if out is None:
             out = torch.empty((int(netH), int(netW), 4), device=torch.device("cuda", torch.cuda.current_device()),
                               dtype=torch.uint8)
+        self._after_torch(out)
         check(lib().vsc_stabilizer_flow_input(self._h, int(window_index), _u8(out, "out"), int(netW), int(netH)))
+        self._before_torch()
         return out
 
     def prefetch_flow_files(self, flow_dir: str, current_frame: int):
@@ -332,6 +358,7 @@ class Stabilizer:
 
     def sync(self):
         check(lib().vsc_stabilizer_sync(self._h))
+        self._inflight.clear()
 
     def reset(self):
         check(lib().vsc_stabilizer_reset(self._h))
@@ -343,9 +370,10 @@ class Stabilizer:
     def last_output(self) -> torch.Tensor:
         """fp32 result of the last step (a copy), [H,W,3] on the device."""
         out = torch.empty((self.H, self.W, 3), device="cuda", dtype=torch.float32)
-        torch.cuda.synchronize()
+        self._after_torch(out)
         check(lib().vsc_stabilizer_copy_last_output(self._h, C.c_void_p(out.data_ptr())))
-        self.sync()
+        self._before_torch()
+        self.sync()      # (also delivers pending 8-bit results to pageable host buffers)
         return out
 
 

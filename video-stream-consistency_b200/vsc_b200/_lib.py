@@ -54,6 +54,7 @@ PROTOTYPES = {
     "vsc_stabilizer_prefetch_flow_files": (_i, [_p, C.c_char_p, _i]),
     "vsc_stabilizer_flow_input": (_i, [_p, _i, _p, _i, _i]),
     "vsc_stabilizer_sync": (_i, [_p]),
+    "vsc_stabilizer_wait_uploads": (_i, [_p]),
     "vsc_stabilizer_last_output_dev": (_p, [_p]),
     "vsc_stabilizer_copy_last_output": (_i, [_p, _p]),
     "vsc_stabilizer_compute_stream": (_p, [_p]),
