@@ -632,7 +632,7 @@ def bench_ours(args, rank, world):
                                                               "us_per_launch", "fused_stage_a", "unblocked_sweep",
                                                               "custom_ops")}}
             if not args.no_cpu_baseline:
-                rec["cpu_baseline"] = cpu_baseline(wlx, args, frames=2, band_h=wlx["H"] // 8)
+                rec["cpu_baseline"] = cpu_baseline(wlx, args, seconds=6.0, band_h=wlx["H"] // 8)
             extras.append(rec)
         result["extra"] = extras
     if world > 1:
@@ -688,7 +688,9 @@ def cpu_state(O, wl, band_h):
     return st
 
 
-def cpu_baseline(wl, args, frames=None, band_h=None):
+def cpu_baseline(wl, args, seconds=10.0, band_h=None):
+    """the CPU arm on a bounded sample: whole frames (or a horizontal band of the frame above 1080p) repeated
+    until about `seconds` of CPU work have been timed"""
     from oracle import oracle as O
 
     H = wl["H"]
@@ -696,11 +698,14 @@ def cpu_baseline(wl, args, frames=None, band_h=None):
     band_h -= band_h % 2
     st = cpu_state(O, wl, band_h)
     cpu_frame(O, wl, band_h, st)  # warm-up
-    n = frames or (5 if band_h == H and H <= 1080 else 4)
+    n = 0
     t0 = time.perf_counter()
-    for _ in range(n):
+    while True:
         cpu_frame(O, wl, band_h, st)
-    dt = time.perf_counter() - t0
+        n += 1
+        dt = time.perf_counter() - t0
+        if (dt >= seconds and n >= 3) or n >= 400:
+            break
     fps = n / dt * (band_h / H)
     return {"value": fps, "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"{n} frames of a {wl['W']}x{band_h} band ({band_h}/{H} of the frame, scaled linearly); "

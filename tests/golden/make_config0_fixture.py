@@ -88,15 +88,13 @@ def refgpu(path):
     st = O.RefGpuStepper(W, H, 3, 2)
     last = pf[2].clone()       # preloadProcessedFrames: lastStabilizedFrame <- processedFrames.back()
     lat = np.zeros((len(c["flows"]), (H + LATTICE - 1) // LATTICE, (W + LATTICE - 1) // LATTICE, 4), np.uint8)
-    f32 = np.zeros(lat.shape[:3] + (3,), np.float32)
     for i, (ff, fb) in enumerate(c["flows"]):
         t = i + 1
-        co, rgba = st.step(of[t - 1], of[t], of[t + 1], pf[t - 1], pf[t], pf[t + 1], last,
+        _, rgba = st.step(of[t - 1], of[t], of[t + 1], pf[t - 1], pf[t], pf[t + 1], last,
                            torch.from_numpy(ff).to(dev), torch.from_numpy(fb).to(dev))
         lat[i] = rgba[::LATTICE, ::LATTICE]
-        f32[i] = co[::LATTICE, ::LATTICE]
     st.close()
-    np.savez_compressed(path, lattice=np.int32(LATTICE), rgba=lat, f32=f32,
+    np.savez_compressed(path, lattice=np.int32(LATTICE), rgba=lat,
                         gpu_name=np.array(torch.cuda.get_device_name(0)))
     print(path, os.path.getsize(path), "bytes")
 
