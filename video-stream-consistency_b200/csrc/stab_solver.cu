@@ -172,10 +172,14 @@ static int launch_prepare(const float* pr, const float* tgt, const float* wt, co
 // implemented in stab_solver_stream.cu: T sweeps per launch, T in {8, 4}
 int solver_stream_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st);
+// implemented in stab_solver_rolled.cu: the same passes with a 4-step loop (16-byte aligned rows); false = not applicable
+bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
+    const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st, int* rc);
+extern int g_stream_rolled;
 
 int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
-extern int g_stream_band;
+extern int g_stream_band, g_stream_edge_top, g_stream_edge_bot;
 bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
 int g_stream_tmain = 0;                     // sweeps per main blocked pass: 0 = chosen per solve, else 8 or 10
@@ -221,7 +225,9 @@ static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, i
     int rc = VSC_OK;
     const int npass = plan.n8 + (plan.tail ? 1 : 0);
     for (int k = 0; k < npass && rc == VSC_OK; ++k) {
-        rc = solver_stream_pass(k < plan.n8 ? plan.tmain : plan.tail, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
+        const int T = k < plan.n8 ? plan.tmain : plan.tail;
+        if (!solver_rolled_pass(T, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st, &rc))
+            rc = solver_stream_pass(T, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
         float* t = src; src = dst; dst = t;
         t = us; us = ud; ud = t;
     }
@@ -286,15 +292,19 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 
 extern "C" int vsc_set_solver_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 2 || mode > 0x37FF || (mode & 0x800) || ((mode >> 8) & 7) > 4 || ((mode >> 12) & 3) > 2)
+    const int lo = mode & 0xFFFF;
+    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0x4800) || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2 || (mode >> 28))
         return VSC_E_INVALID;
-    g_solver_mode = mode & 0xF;
-    g_stream_pair = (mode & 0x10) == 0;
-    g_stream_coop = (mode & 0x20) == 0;
-    g_frame_fused = (mode & 0x40) == 0;
-    g_pdl = (mode & 0x80) == 0;
-    g_stream_tmain = ((mode >> 12) & 3) == 0 ? 0 : 6 + 2 * ((mode >> 12) & 3);
-    g_stream_band = (mode >> 8) & 7;
+    g_solver_mode = lo & 0xF;
+    g_stream_pair = (lo & 0x10) == 0;
+    g_stream_coop = (lo & 0x20) == 0;
+    g_frame_fused = (lo & 0x40) == 0;
+    g_pdl = (lo & 0x80) == 0;
+    g_stream_tmain = ((lo >> 12) & 3) == 0 ? 0 : 6 + 2 * ((lo >> 12) & 3);
+    g_stream_band = (lo >> 8) & 7;
+    g_stream_rolled = (lo & 0x8000) ? 0 : 1;
+    g_stream_edge_top = ((mode >> 16) & 0x3F) - 1;   // 0 = default
+    g_stream_edge_bot = ((mode >> 22) & 0x3F) - 1;
     return VSC_OK;
 }
 

@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libvsc_b200.so")
+# VSC_B200_LIB: another build of the SAME library (profiles/build_variant.py compiles csrc/ with extra -D flags for
+# A/B timing of kernel variants); it must export every symbol below like the default build.
+LIB_PATH = os.environ.get("VSC_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libvsc_b200.so")
 
 
 class VscError(RuntimeError):
