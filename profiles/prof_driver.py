@@ -78,7 +78,7 @@ if "warp" in which:
     for (C, h, w) in ((32, 544, 960), (64, 272, 480), (96, 136, 240), (64, 72, 120)):
         x = rnd(1, C, h, w)
         f = torch.from_numpy(synth.op_flow_smooth(1, h, w, 3)).to(dev)
-        for mode in (1, 2, 3):   # linear, tiled quad, linear quad
+        for mode in (1, 2, 3, 4 | (1 << 4)):   # linear, tiled quad, linear quad, TMA-staged (all channels per CTA)
             V.check(V.lib().vsc_set_warp_mode(mode))
             for _ in range(2):
                 V.warp(x, f)

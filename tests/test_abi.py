@@ -78,9 +78,9 @@ def test_kernel_selection_words_are_validated(V):
     for bad in (-1, 5, 0x203, 0x403, 0x803, 1 << 20):
         assert L.vsc_set_stage_a_mode(bad) == -1, hex(bad)
     assert L.vsc_set_stage_a_mode(0) == 0
-    for ok in (0, 1, 2, 3, 1 | (1 << 4), 1 | (255 << 4)):
+    for ok in (0, 1, 2, 3, 4, 4 | (2 << 4), 1 | (1 << 4), 1 | (255 << 4)):
         assert L.vsc_set_warp_mode(ok) == 0, hex(ok)
-    for bad in (-1, 4, 5, 0x1001):
+    for bad in (-1, 5, 6, 0x1001):
         assert L.vsc_set_warp_mode(bad) == -1, hex(bad)
     assert L.vsc_set_warp_mode(0) == 0
 

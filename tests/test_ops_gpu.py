@@ -108,7 +108,8 @@ def test_correlation_full_size_properties(V, dev):
 
 
 # ---------------------------------------------------------------- Warp
-@pytest.fixture(params=[1, 2, 3, 1 | (2 << 4)], ids=["linear", "tiled", "linear-quad", "linear-2chunks"])
+@pytest.fixture(params=[0, 1, 2, 3, 1 | (2 << 4), 4, 4 | (3 << 4)],
+                ids=["auto", "linear", "tiled", "linear-quad", "linear-2chunks", "tma-staged", "tma-staged-3chunks"])
 def warp_mode(V, request):
     """every Warp test runs on both kernels (vsc_set_warp_mode)"""
     assert V.lib().vsc_set_warp_mode(request.param) == 0
@@ -175,9 +176,12 @@ def test_warp_kernels_agree(V, dev):
     """the tiled kernel (shared 2x2 gather quad, border corners re-slotted) equals the one-pixel-per-thread
     kernel value for value, including every border case a large random flow produces"""
     g = torch.Generator(device=dev).manual_seed(17)
-    for (N, C, H, W) in ((2, 12, 67, 131), (1, 7, 5, 3), (1, 4, 2, 2), (1, 33, 40, 64), (2, 9, 41, 100), (1, 5, 70, 33)):
+    # (the shapes with W % 4 == 0, W >= 72, H >= 12 run the TMA-staged kernel in mode 4: smooth flow -> staged tiles,
+    # random flow -> its gather path, and (50, 148) / (33, 200) have partial tiles at the right and bottom edges)
+    for (N, C, H, W) in ((2, 12, 67, 131), (1, 7, 5, 3), (1, 4, 2, 2), (1, 33, 40, 64), (2, 9, 41, 100), (1, 5, 70, 33),
+                         (2, 13, 50, 148), (1, 8, 33, 200), (1, 32, 136, 240), (2, 6, 64, 128)):
         x = torch.randn((N, C, H, W), device=dev, generator=g)
-        if (H, W) in ((41, 100), (70, 33)):
+        if (H, W) in ((41, 100), (70, 33), (50, 148), (136, 240)):
             # smooth flow: neighbouring lanes sample neighbouring taps (the shuffle kernel's fast path), with a few
             # NaN / huge displacements so that live and dead lanes alternate inside a warp
             f = torch.from_numpy(synth.op_flow_smooth(N, H, W, 3, amp=3.0, noise=0.05)).to(dev)
@@ -197,13 +201,20 @@ def test_warp_kernels_agree(V, dev):
             d = V.warp(x, f)
             assert V.lib().vsc_set_warp_mode(1 | (5 << 4)) == 0   # 5 channel chunks
             e = V.warp(x, f)
+            assert V.lib().vsc_set_warp_mode(4) == 0              # TMA-staged tiles where applicable
+            s4 = V.warp(x, f)
+            assert V.lib().vsc_set_warp_mode(4 | (2 << 4)) == 0
+            s5 = V.warp(x, f)
         finally:
             V.lib().vsc_set_warp_mode(0)
         assert torch.equal(a, b), (N, C, H, W)
         assert torch.equal(a, c), (N, C, H, W)
         assert torch.equal(a, d), (N, C, H, W)
         assert torch.equal(a, e), (N, C, H, W)
-    assert V.lib().vsc_set_warp_mode(4) == -1
+        # NaN != NaN: compare bit patterns
+        assert torch.equal(a.view(torch.int32), s4.view(torch.int32)), (N, C, H, W)
+        assert torch.equal(a.view(torch.int32), s5.view(torch.int32)), (N, C, H, W)
+    assert V.lib().vsc_set_warp_mode(5) == -1
 
 
 def test_ops_reject_bad_arguments(V, dev):

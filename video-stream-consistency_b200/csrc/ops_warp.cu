@@ -9,76 +9,9 @@
 // `mask > 0.999` threshold falls identically), and then streams over a chunk of channels doing
 // only gathers + 4 fp32 multiply-adds per value.  HBM traffic = the algorithmic
 // 4*N*H*W*(2C+2) bytes (gathers hit L1/L2: neighbouring pixels sample neighbouring taps).
-#include "vsc_common.cuh"
+#include "ops_warp.cuh"
 
 namespace vsc {
-
-struct WarpTap {
-    int o00, o10, o01, o11;      // element offsets inside one H*W plane (0 when the corner is unused)
-    float w00, w10, w01, w11;    // bilinear weights (0 when unused)
-    unsigned valid;              // bit k set: corner k is read
-};
-
-// geometry of one output pixel, following warp.cc:85-129 / warp_cuda.cu:42-81 type by type
-__device__ __forceinline__ WarpTap warp_setup(int x, int y, float fu, float fv, int W, int H)
-{
-    WarpTap t;
-    const float xf = static_cast<float>(x) + fu;
-    const float yf = static_cast<float>(y) + fv;
-    const float xL = floorf(xf);
-    const float yT = floorf(yf);
-    const float alpha = xf - xL;
-    const float beta = yf - yT;
-    const float right_edge = static_cast<float>(W - 1);
-    const float bottom_edge = static_cast<float>(H - 1);
-    const float xR = xL + 1.0f;  // == float(double(xL) + 1.0): one rounding of the exact sum
-    const float yB = yT + 1.0f;
-    const bool mL = (0.0f <= xL && xL <= right_edge);
-    const bool mR = (0.0f <= xR && xR <= right_edge);
-    const bool mT = (0.0f <= yT && yT <= bottom_edge);
-    const bool mB = (0.0f <= yB && yB <= bottom_edge);
-    // products in double, each += rounded back to float (the reference's mixed types)
-    const double a1 = 1.0 - static_cast<double>(alpha);
-    const double b1 = 1.0 - static_cast<double>(beta);
-    const double d00 = a1 * b1;
-    const double d10 = static_cast<double>(alpha) * b1;
-    const double d01 = a1 * static_cast<double>(beta);
-    const double d11 = static_cast<double>(alpha * beta);  // float*float first, as `(alpha) * (beta)` evaluates
-    float mask = 0.0f;
-    mask = static_cast<float>(static_cast<double>(mask) + d00 * ((mT && mL) ? 1.0 : 0.0));
-    mask = static_cast<float>(static_cast<double>(mask) + d10 * ((mT && mR) ? 1.0 : 0.0));
-    mask = static_cast<float>(static_cast<double>(mask) + d01 * ((mB && mL) ? 1.0 : 0.0));
-    mask = static_cast<float>(static_cast<double>(mask) + d11 * ((mB && mR) ? 1.0 : 0.0));
-    const bool keep = static_cast<double>(mask) > 0.999;
-    const bool v00 = keep && mT && mL, v10 = keep && mT && mR, v01 = keep && mB && mL, v11 = keep && mB && mR;
-    // integer coordinates are only formed for corners that passed the range test
-    const int ixL = mL ? static_cast<int>(xL) : 0, ixR = mR ? static_cast<int>(xR) : 0;
-    const int iyT = mT ? static_cast<int>(yT) : 0, iyB = mB ? static_cast<int>(yB) : 0;
-    t.o00 = v00 ? iyT * W + ixL : 0;
-    t.o10 = v10 ? iyT * W + ixR : 0;
-    t.o01 = v01 ? iyB * W + ixL : 0;
-    t.o11 = v11 ? iyB * W + ixR : 0;
-    t.w00 = v00 ? static_cast<float>(d00) : 0.0f;
-    t.w10 = v10 ? static_cast<float>(d10) : 0.0f;
-    t.w01 = v01 ? static_cast<float>(d01) : 0.0f;
-    t.w11 = v11 ? static_cast<float>(d11) : 0.0f;
-    t.valid = (v00 ? 1u : 0u) | (v10 ? 2u : 0u) | (v01 ? 4u : 0u) | (v11 ? 8u : 0u);
-    return t;
-}
-
-__device__ __forceinline__ float warp_sample(const float* __restrict__ plane, const WarpTap& t)
-{
-    // unused corners are not read (their storage may hold non-finite values)
-    const float a = (t.valid & 1u) ? __ldg(plane + t.o00) : 0.0f;
-    const float b = (t.valid & 2u) ? __ldg(plane + t.o10) : 0.0f;
-    const float c = (t.valid & 4u) ? __ldg(plane + t.o01) : 0.0f;
-    const float d = (t.valid & 8u) ? __ldg(plane + t.o11) : 0.0f;
-    float v = t.w00 * a;
-    v = v + t.w10 * b;
-    v = v + t.w01 * c;
-    v = v + t.w11 * d;
-    return v;
-}
 
 // grid: x = 256-pixel groups of one image, y = channel chunk, z = n.  One pixel per thread: the 32 lanes of a
 // warp sample 32 neighbouring positions, so each of the four gathers touches a handful of 32-byte sectors and
@@ -215,9 +148,9 @@ __global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_quad_kernel
         const float vc = uC ? __ldg(b) : 0.0f;
         const float vd = uD ? __ldg(b + 1) : 0.0f;
         float v = q.wA * va;
-        v = v + q.wB * vb;
-        v = v + q.wC * vc;
-        v = v + q.wD * vd;
+        v = __fmaf_rn(q.wB, vb, v);
+        v = __fmaf_rn(q.wC, vc, v);
+        v = __fmaf_rn(q.wD, vd, v);
         return v;
     };
     int c = c0;
@@ -247,7 +180,13 @@ __global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_quad_kernel
         __stcs(op, sample(pt, pb));
 }
 
-int g_warp_mode = 0;    // 0 default (= 1), 1 linear one-pixel-per-thread kernel, 2 tiled, 3 quad addressing, flattened
+int g_warp_mode = 0;    // 0 default, 1 linear one-pixel-per-thread kernel, 2 tiled, 3 quad addressing, flattened,
+                        // 4 TMA-staged tiles wherever applicable (ops_warp_staged.cu)
+bool warp_staged_applicable(const float* in, int N, int C, int H, int W);
+int launch_warp_staged(const float* in, const float* flow, float* out, int N, int C, int H, int W, int nchunk_req,
+    cudaStream_t st, bool* launched);
+// smallest map the staged kernel takes by default (measured: profiles/r2_warp_staged_events.txt)
+constexpr long long kWarpStagedMinPixels = 120000;
 int g_warp_nchunk = 0;  // 0 = automatic channel split of the linear kernel, else the number of channel chunks
 
 }  // namespace vsc
@@ -265,6 +204,14 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     // measured (profiles/r1_time_ops_v13.txt, r1_warp_linear_vs_tiled_ncu.txt): on smooth flow -- what an optical-flow
     // network produces -- the linear kernel is 4-16 % faster at every level shape; the tiled one wins only on
     // scattered flow (i.i.d. sigma = 2 px: 53 vs 59 us at 32x544x960).  Default: linear; tiled on request.
+    // large maps with 16-byte aligned rows: tiles staged in shared memory by TMA (gathers for tiles with scattered flow)
+    const bool big = static_cast<long long>(H) * W >= kWarpStagedMinPixels;
+    if ((g_warp_mode == 4 || (g_warp_mode == 0 && big)) && warp_staged_applicable(in, N, C, H, W)) {
+        bool launched = false;
+        const int rc = launch_warp_staged(in, flow, out, N, C, H, W, g_warp_nchunk, as_stream(stream), &launched);
+        if (rc || launched)
+            return rc;
+    }
     if (g_warp_mode == 2 || g_warp_mode == 3) {
         const bool tiled = g_warp_mode == 2;
         const unsigned tx = tiled ? cdiv(W, kWarpTileW) : cdiv(static_cast<long long>(H) * W, 256);
@@ -307,7 +254,7 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
 
 extern "C" int vsc_set_warp_mode(int mode)
 {
-    if (mode < 0 || (mode & 0xF) > 3 || mode > 0xFFF)
+    if (mode < 0 || (mode & 0xF) > 4 || mode > 0xFFF)
         return VSC_E_INVALID;
     vsc::g_warp_mode = mode & 0xF;
     vsc::g_warp_nchunk = mode >> 4;

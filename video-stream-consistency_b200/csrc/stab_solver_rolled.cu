@@ -6,7 +6,7 @@
 // Why.  In stab_solver_stream.cu every ring index is a compile-time constant because the step loop is unrolled over
 // the longest ring period, 2T steps (the per-row coefficients A, B live 2T steps in registers).  At T = 10 that is
 // 2470 instructions = 39.5 KB of hot loop, plus a second copy with the top/bottom row masks: more than the 32 KB
-// instruction cache.  ncu (profiles/r2_solver_icache.txt): a quarter of the warp samples INSIDE the hot loop are
+// instruction cache.  ncu (profiles/r2_solver_notes.md, r2_solver_fillspec_ncu.txt): a quarter of the warp samples INSIDE the hot loop are
 // `no_instruction`, and code that a CTA executes only once (the masked copy in the image's first and last row chunk;
 // an experiment that compiled the pipeline-fill steps without their idle levels: 12 % fewer instructions, 45 %
 // SLOWER) costs twice as much per instruction as resident code.  Here only the period-4 rings (row windows, exchange
@@ -15,7 +15,7 @@
 // the staging slot is a run-time base advanced once per group.  Hot loop: 4 steps = about 560 instructions = 9 KB,
 // masked copy the same -- the whole kernel stays resident.
 //
-// Also here (all measured in profiles/r2_solver_sweep.txt):
+// Also here (all measured in profiles/r2_solver_notes.md):
 //   * the momentum ring is two rows deep instead of four (20 registers at T = 10, which pay for the coefficient
 //     window's four extra rows);
 //   * staging hand-off by the exchange barrier instead of a per-step cp.async wait + __syncwarp: rows are requested
@@ -244,7 +244,7 @@ static RolledGeom rolled_geom(int T, int BW, int L, int H, int sms)
     const int min_rows = 4 * T;  // below this the 3T-step pipeline fill dominates
     if (nc > (H + min_rows - 1) / min_rows) nc = (H + min_rows - 1) / min_rows;
     if (nc < 1) nc = 1;
-    // the first / last chunk run the masked copy for 3T / 2T steps: shorter by default (profiles/r2_solver_sweep.txt)
+    // the first / last chunk run the masked copy for 3T / 2T steps: shorter by default (profiles/r2_solver_sweep_pairs_edges.txt)
     int top = g_stream_edge_top >= 0 ? g_stream_edge_top : 8, bot = g_stream_edge_bot >= 0 ? g_stream_edge_bot : 4;
     if (nc < 3 || H < nc * (2 * T + top + bot)) top = bot = 0;
     // H = (mid - top) + (nc - 2) * mid + last,  last <= mid - bot
