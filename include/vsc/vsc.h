@@ -221,6 +221,16 @@ VSC_API int vsc_frame_stabilize(const float* origPrev, const float* origCur, con
 typedef struct vsc_stabilizer vsc_stabilizer;
 
 VSC_API int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flow_channels);
+/* the same with flow batches (main.cpp:48-63 `-b batchSize`, videostabilizer.cpp:65-71,136-153,176,269-273): the
+ * window holds 2k + batchSize frames (k = 1; batchSize 1..16), lastStabilizedFrame is initialised from the LAST
+ * preloaded frame (the (2 + batchSize)-th push), a step consumes window[0..2] as before, and
+ * vsc_stabilizer_flow_input accepts window indices up to 1 + batchSize, so that a flow session can fill its
+ * [batchSize, H, W, 4] inputs with frames 1..batchSize / 2..batchSize+1 once every batchSize steps.
+ * vsc_stabilizer_create == batchSize 1. */
+VSC_API int vsc_stabilizer_create_batched(vsc_stabilizer** out, int W, int H, int flow_channels, int batchSize);
+VSC_API int vsc_stabilizer_batch_size(const vsc_stabilizer* s);
+/* frames currently in the window */
+VSC_API int vsc_stabilizer_window_count(const vsc_stabilizer* s);
 VSC_API void vsc_stabilizer_destroy(vsc_stabilizer* s);
 /* live pointer, like VideoStabilizer::getHyperParams(); snapshotted once per step (:192) */
 VSC_API vsc_hyper_params* vsc_stabilizer_hyper_params(vsc_stabilizer* s);
@@ -246,7 +256,7 @@ VSC_API int vsc_stabilizer_push_frame(vsc_stabilizer* s, const uint8_t* orig_rgb
  * doOneStep(): stabilise window[1] with flow cur->next (flowFwd) and the flow the reference uses
  * as cur->prev (flowBwd), both DEVICE HWC images of flow_channels channels at frame resolution.
  * Writes the RGBA8888 result to out_rgba_host (if non-NULL; valid after vsc_stabilizer_sync),
- * updates lastStabilizedFrame and pops the window front.  Requires 3 frames in the window. */
+ * updates lastStabilizedFrame and pops the window front.  Requires at least 3 frames in the window. */
 VSC_API int vsc_stabilizer_step(vsc_stabilizer* s, const float* flowFwd_dev, const float* flowBwd_dev,
     uint8_t* out_rgba_host);
 /* same, flows given at a lower resolution (FLOWDOWNSCALE, flowmodel.cpp:156-165): upsampled with
@@ -270,9 +280,9 @@ VSC_API int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flow_d
  * memory (file reading overlaps the previous frame's GPU work).  Read errors surface from that step call. */
 VSC_API int vsc_stabilizer_prefetch_flow_files(vsc_stabilizer* s, const char* flow_dir, int currentFrame);
 /* FlowModel::run input path without the host (flowmodel.cpp:121-150): writes window frame `window_index`
- * (0 = previous, 1 = current, 2 = next; the ORIGINAL stream) as RGBA8888 at netW x netH into dst_dev -- e.g. the
+ * (0 = previous, 1 = current, 2 = next, ... up to 1 + batchSize; the ORIGINAL stream) as RGBA8888 at netW x netH into dst_dev -- e.g. the
  * flow session's bound input tensor -- scaling with vsc_rgba8_scale_nearest when the size differs.  Enqueued on
- * the compute stream; requires 3 frames in the window. */
+ * the compute stream; the window must hold that frame. */
 VSC_API int vsc_stabilizer_flow_input(vsc_stabilizer* s, int window_index, uint8_t* dst_dev, int netW, int netH);
 VSC_API int vsc_stabilizer_sync(vsc_stabilizer* s);
 /* blocks until every host->device copy enqueued so far (frames of vsc_stabilizer_push_frame, flows of

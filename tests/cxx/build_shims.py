@@ -47,6 +47,18 @@ def build_host_shims(force: bool = False):
                       os.path.join(ROOT, "tests", "cxx", "stab_shim_driver.cpp")],
                      ["-I", REF_STAB, "-I", os.path.join(ROOT, "standins", "qt"), "-I", CUDA_INC],
                      ["-lvsc_b200", "-L", CUDA_LIB, f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"]))
+        # the VideoStabilizer drop-in: the product's vsc_videostabilizer.cpp against the reference's unmodified
+        # videostabilizer.h (+ flowmodel.h, imagehelpers.h, the inference headers), the reference's own
+        # imagehelpers.cpp compiled as it is, the GPUImage / flowconsistency shim, and a driver that plays the
+        # StreamStabilizer subclass and the flow network
+        jobs.append((os.path.join(TEST_SO_DIR, "libvsc_videostab_test.so"),
+                     [os.path.join(HERE, "host", "stabilization", "vsc_videostabilizer.cpp"),
+                      os.path.join(HERE, "host", "stabilization", "vsc_flowconsistency.cpp"),
+                      os.path.join(REF_STAB, "imagehelpers.cpp"),
+                      os.path.join(ROOT, "tests", "cxx", "videostab_driver.cpp")],
+                     ["-I", REF_STAB, "-I", os.path.dirname(REF_STAB), "-I", os.path.join(ROOT, "standins", "qt"),
+                      "-I", CUDA_INC],
+                     ["-lvsc_b200", "-L", CUDA_LIB, f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"]))
     for out, srcs, inc, libs in jobs:
         deps = srcs + [LIB] + [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "standins")) for f in fs] \
             + [os.path.join(HERE, "host", "inference", "vsc_flow_session.h")]

@@ -68,7 +68,14 @@ extern "C" {
 
 const char* vsc_fs_test_last_error() { return g_error.c_str(); }
 
+void* vsc_fs_test_create_b(int W, int H, int netW, int netH, const char* model_path, int batch_directions, int batch_size);
 void* vsc_fs_test_create(int W, int H, int netW, int netH, const char* model_path, int batch_directions)
+{
+    return vsc_fs_test_create_b(W, H, netW, netH, model_path, batch_directions, 1);
+}
+
+// batch_size = the CLI's -b: window of 2 + batch_size frames, [batch_size, H, W, 4] session tensors
+void* vsc_fs_test_create_b(int W, int H, int netW, int netH, const char* model_path, int batch_directions, int batch_size)
 {
     try {
         OrtStandinGraphs()[kModel] = graph_fn;
@@ -83,11 +90,11 @@ void* vsc_fs_test_create(int W, int H, int netW, int netH, const char* model_pat
                 || cudaMalloc(reinterpret_cast<void**>(&g_graph.b), g_graph.px * 12) != cudaSuccess)
                 throw std::runtime_error("driver: cudaMalloc failed");
         }
-        const int rc = vsc_stabilizer_create(&rig->st, W, H, 3);
+        const int rc = vsc_stabilizer_create_batched(&rig->st, W, H, 3, batch_size);
         if (rc)
             throw std::runtime_error(vsc_error_string(rc));
         rig->fs = std::make_unique<VscFlowSession>(rig->env, model_path ? model_path : kModel, netW, netH, rig->st, 0,
-            batch_directions != 0);
+            batch_directions != 0, batch_size);
         return rig.release();
     } catch (const std::exception& e) {
         g_error = e.what();

@@ -9,6 +9,9 @@
 
 #include <cuda_runtime.h>
 
+#include <malloc.h>
+
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <exception>
@@ -24,6 +27,19 @@ struct Stab {
     std::vector<std::unique_ptr<GPUImage>> pyrPr, pyrAdapCmbPr, pyrConsWt, pyrConsisOut;
 };
 std::unique_ptr<GPUImage> mk(int w, int h, int c) { return std::unique_ptr<GPUImage>(new GPUImage(w, h, c)); }
+}  // namespace
+
+namespace {
+// 4K frames are 33 MB: above glibc's largest dynamic mmap threshold (32 MB), so every QImage of the application
+// would be a fresh mmap whose pages fault in on first touch (8 ms per frame and image) and are unmapped on free.
+// The timing runs keep such blocks on the heap, as a long-running player's allocator does; it changes no result.
+struct HeapForFrames {
+    HeapForFrames()
+    {
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    }
+} g_heap_for_frames;
 }  // namespace
 
 extern "C" {
@@ -102,6 +118,66 @@ int vsc_shim_push(void* p, const unsigned char* orig_rgba, const unsigned char* 
         return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "vsc_shim_push: %s\n", e.what());
+        return 1;
+    }
+}
+
+// TIMING: `reps` times the doOneStep call sequence from the flow copies to copyToQImage (videostabilizer.cpp:177-238)
+// on the window as it stands (nothing is popped); flows are uploaded once before.  Returns host-clock ms per step in
+// *ms_per_step.  Every shim call is synchronous, like the reference's.
+int vsc_shim_time_steps(void* p, const float* flowFwd_host, const float* flowBwd_host, int reps, int numIter,
+    double* ms_per_step)
+{
+    try {
+        Stab& s = *static_cast<Stab*>(p);
+        if (s.orig.size() != 3)
+            return 3;
+        const int W = s.W, H = s.H;
+        GPUImage resF(W, H, s.flowC), resB(W, H, s.flowC);   // flowResultsFwd/Bwd[batchIdx]
+        resF.copyFrom(std::vector<float>(flowFwd_host, flowFwd_host + static_cast<size_t>(W) * H * s.flowC));
+        resB.copyFrom(std::vector<float>(flowBwd_host, flowBwd_host + static_cast<size_t>(W) * H * s.flowC));
+        const int levels = static_cast<int>(s.pyrPr.size());
+        cudaDeviceSynchronize();
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; ++r) {
+            s.flowFwd->copyFrom(resF);
+            s.flowBwd->copyFrom(resB);
+            get_warp_result(*s.orig[0], *s.flowBwd, *s.prevWarpIn);
+            get_warp_result(*s.proc[0], *s.flowBwd, *s.prevWarpPr);
+            get_warp_result(*s.orig[2], *s.flowFwd, *s.nextWarpIn);
+            get_warp_result(*s.proc[2], *s.flowFwd, *s.nextWarpPr);
+            get_warp_result(*s.last, *s.flowBwd, *s.lastStabWarp);
+            get_adap_comb(*s.orig[1], *s.proc[1], *s.prevWarpIn, *s.prevWarpPr, *s.nextWarpIn, *s.nextWarpPr,
+                *s.adapCmbIn, *s.adapCmbPr, *s.lastStabWarp, 6800.0f);
+            get_consist_wt(*s.adapCmbIn, *s.orig[1], *s.consWt, 6800.0f, 2.0f);
+            for (int j = 0; j < levels; ++j) {
+                if (j == 0) {
+                    s.pyrPr[0]->copyFrom(*s.proc[1]);
+                    s.pyrAdapCmbPr[0]->copyFrom(*s.adapCmbPr);
+                    s.pyrConsWt[0]->copyFrom(*s.consWt);
+                    s.pyrConsisOut[0]->copyFrom(*s.proc[1]);
+                } else {
+                    get_bilinear(*s.pyrPr[j - 1], *s.pyrPr[j]);
+                    get_bilinear(*s.pyrAdapCmbPr[j - 1], *s.pyrAdapCmbPr[j]);
+                    get_bilinear(*s.pyrConsWt[j - 1], *s.pyrConsWt[j]);
+                    get_bilinear(*s.pyrConsisOut[j - 1], *s.pyrConsisOut[j]);
+                }
+            }
+            for (int j = levels - 1; j >= 0; --j) {
+                if (j != levels - 1)
+                    get_bilinear(*s.pyrConsisOut[j + 1], *s.pyrConsisOut[j]);
+                get_consist_out(*s.pyrPr[j], *s.pyrAdapCmbPr[j], *s.pyrConsWt[j], numIter / (j + 1), 0.15f, 0.15f,
+                    *s.pyrConsisOut[j]);
+            }
+            s.consisOut->copyFrom(*s.pyrConsisOut[0]);
+            QImage q(W, H, QImage::Format_RGBA8888);   // a fresh image per frame, as videostabilizer.cpp:237
+            s.consisOut->copyToQImage(q);
+            s.last->copyFrom(*s.consisOut);
+        }
+        *ms_per_step = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "vsc_shim_time_steps: %s\n", e.what());
         return 1;
     }
 }

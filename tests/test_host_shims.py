@@ -160,6 +160,8 @@ def fs():
     lib.vsc_fs_test_last_error.restype = C.c_char_p
     lib.vsc_fs_test_create.restype = C.c_void_p
     lib.vsc_fs_test_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    lib.vsc_fs_test_create_b.restype = C.c_void_p
+    lib.vsc_fs_test_create_b.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int]
     lib.vsc_fs_test_destroy.argtypes = [C.c_void_p]
     lib.vsc_fs_test_stabilizer.restype = C.c_void_p
     lib.vsc_fs_test_stabilizer.argtypes = [C.c_void_p]
@@ -257,7 +259,163 @@ def test_flow_session_runs_on_device_buffers(fs, V, dev, W, H, scale, batched):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batch", [2, 3])
+def test_flow_session_flow_batches(fs, V, dev, batch):
+    """`-b batchSize` through VscFlowSession: [batchSize,H,W,4] session tensors filled on the device from window
+    frames 1..batchSize / 2..batchSize+1, ONE run per direction every batchSize frames, the frames in between index
+    into the two flow batches (videostabilizer.cpp:176-179,269-273; flowmodel.cpp:137-165).  Stabilized frames equal a
+    batch-1 Python-binding run that starts its recurrence from the same frame, bit for bit."""
+    import torch
+
+    W, H, netW, netH, T = 96, 64, 48, 32, 10
+    o8, p8 = synth.frames(W, H, T, seed=81)
+    before = _fs_counters(fs)
+    rig = fs.vsc_fs_test_create_b(W, H, netW, netH, None, 0, batch)
+    assert rig, fs.vsc_fs_test_last_error()
+    st = C.c_void_p(fs.vsc_fs_test_stabilizer(rig))
+    L = V.lib()
+    ref = V.Stabilizer(W, H, 3, batch_size=batch)
+    outs, refs = [], []
+
+    def graph(first, second):   # what the stand-in model computes, via the Python binding
+        a = V.image_to_gpu(V.rgba8_scale_nearest(torch.from_numpy(first).to(dev), netW, netH))
+        b = V.image_to_gpu(V.rgba8_scale_nearest(torch.from_numpy(second).to(dev), netW, netH))
+        return V.get_warp_result(a, b)
+
+    nsteps = 2 * batch   # two whole flow batches
+    try:
+        for t in range(2 + batch):
+            assert L.vsc_stabilizer_push_frame(st, o8[t].ctypes.data_as(C.c_void_p), p8[t].ctypes.data_as(C.c_void_p)) == 0
+            ref.push_frame(o8[t], p8[t])
+        for t in range(1, 1 + nsteps):
+            out = np.zeros((H, W, 4), np.uint8)
+            assert fs.vsc_fs_test_step(rig, out.ctypes.data_as(C.c_void_p)) == 0, fs.vsc_fs_test_last_error()
+            assert L.vsc_stabilizer_sync(st) == 0
+            outs.append(out)
+            r = np.zeros((H, W, 4), np.uint8)
+            ref.step(graph(o8[t], o8[t + 1]), graph(o8[t + 1], o8[t]), r)
+            ref.sync()
+            refs.append(r)
+            nxt = t + 1 + batch
+            if nxt < T:
+                assert L.vsc_stabilizer_push_frame(st, o8[nxt].ctypes.data_as(C.c_void_p),
+                                                   p8[nxt].ctypes.data_as(C.c_void_p)) == 0
+                ref.push_frame(o8[nxt], p8[nxt])
+    finally:
+        fs.vsc_fs_test_destroy(rig)
+        ref.close()
+    for a, b in zip(outs, refs):
+        assert np.array_equal(a, b)
+    c = _fs_counters(fs)
+    assert c["runs"] - before["runs"] == 2 * 2                      # two directions per flow batch, two batches
+    assert c["provider_syncs"] - before["provider_syncs"] == 0
+
+
+@pytest.mark.gpu
 def test_flow_session_unknown_model_throws(fs, V, dev):
     """InferenceModelVariant::createSession rethrows ORT's load failure (:175-183); so does the flow session."""
     assert not fs.vsc_fs_test_create(64, 48, 64, 48, b"models/does-not-exist.onnx", 0)
     assert b"does-not-exist" in fs.vsc_fs_test_last_error()
+
+
+# ---------------------------------------------------------------- VideoStabilizer drop-in (host/stabilization/vsc_videostabilizer.cpp)
+@pytest.fixture(scope="module")
+def vs():
+    path = os.path.join(os.path.dirname(__file__), "cxx", "_build", "libvsc_videostab_test.so")
+    if not os.path.exists(path):
+        pytest.skip("libvsc_videostab_test.so not built (needs the reference checkout at build time)")
+    lib = C.CDLL(path)
+    lib.vsc_vs_test_last_error.restype = C.c_char_p
+    lib.vsc_vs_test_flow_runs.restype = C.c_long
+    lib.vsc_vs_test_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_float]
+    return lib
+
+
+def test_videostabilizer_dropin_library_exports(vs):
+    """CPU: the drop-in TU compiled against the reference's unmodified videostabilizer.h (+ flowmodel.h, imagehelpers.h,
+    the inference headers) and linked with the reference's own imagehelpers.cpp; the library loads and exports its
+    driver."""
+    assert hasattr(vs, "vsc_vs_test_run") and hasattr(vs, "vsc_vs_test_flow_runs")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,scale", [(1, 1), (1, 2), (3, 2), (2, 1)])
+def test_videostabilizer_dropin_sequence(vs, V, O, dev, batch, scale, monkeypatch):
+    """The reference's class VideoStabilizer with the product's member functions: preloadProcessedFrames, doOneStep
+    until the stream ends, outputFinalFrames -- driven like StreamStabilizer::stabilizeAll, with `-b batch` flow batches
+    and FLOWDOWNSCALE.  Every emitted frame equals the same clip run through the pipeline object of the Python binding
+    (same kernels underneath) bit for bit; batch 1 at full flow resolution is also held against the oracle."""
+    import torch
+
+    W, H, T = 96, 64, 9
+    netW, netH = round(W / scale), round(H / scale)
+    o8, p8 = synth.frames(W, H, T, seed=83, mismatch=0.2)
+    if scale > 1:
+        monkeypatch.setenv("FLOWDOWNSCALE", str(scale))
+    else:
+        monkeypatch.delenv("FLOWDOWNSCALE", raising=False)
+    orig = np.ascontiguousarray(np.stack(o8))
+    proc = np.ascontiguousarray(np.stack(p8))
+    outs = np.zeros((T, H, W, 4), np.uint8)
+    have = np.zeros(T, np.int32)
+    runs0 = vs.vsc_vs_test_flow_runs()
+    steps = vs.vsc_vs_test_run(W, H, T, batch, orig.ctypes.data_as(C.c_void_p), proc.ctypes.data_as(C.c_void_p),
+                               outs.ctypes.data_as(C.c_void_p), have.ctypes.data_as(C.c_void_p), 0, 0.0)
+    assert steps > 0, vs.vsc_vs_test_last_error()
+
+    def graph(first, second):   # the driver's stand-in network, via the Python binding
+        a = V.image_to_gpu(V.rgba8_scale_nearest(torch.from_numpy(first).to(dev), netW, netH))
+        b = V.image_to_gpu(V.rgba8_scale_nearest(torch.from_numpy(second).to(dev), netW, netH))
+        return V.get_warp_result(a, b)
+
+    # the same control flow on the pipeline object (videostabilizer.cpp:136-164,167-279)
+    ref = V.Stabilizer(W, H, 3, batch_size=batch)
+    exp, exp_have = np.zeros_like(outs), np.zeros(T, np.int32)
+    win = list(range(2 + batch))
+    nxt = 2 + batch
+    for t in win:
+        ref.push_frame(o8[t], p8[t])
+    for t in (0, 1):   # j <= k
+        exp[t], exp_have[t] = p8[t], exp_have[t] + 1
+    exp[:2, ..., 3] = 1   # gpuToImage writes alpha = 1 (gpuimage.cu:66)
+    i, nsteps, flow_batches = 1, 0, 0
+    ff = fb = None
+    ora = []
+    while True:
+        if (i - 1) % batch == 0:
+            ff = [graph(o8[win[1 + b]], o8[win[2 + b]]) for b in range(batch)]
+            fb = [graph(o8[win[2 + b]], o8[win[1 + b]]) for b in range(batch)]
+            flow_batches += 1
+        out = np.zeros((H, W, 4), np.uint8)
+        bi = (i - 1) % batch
+        ora.append((win[0], win[1], win[2], ff[bi], fb[bi]))
+        ref.step(ff[bi], fb[bi], out)
+        ref.sync()
+        exp[i], exp_have[i] = out, exp_have[i] + 1
+        nsteps += 1
+        win.pop(0)
+        if nxt < T:
+            ref.push_frame(o8[nxt], p8[nxt])
+            win.append(nxt)
+            nxt += 1
+        else:
+            exp[i + 1], exp_have[i + 1] = p8[win[1]], exp_have[i + 1] + 1   # outputFinalFrames
+            exp[i + 1, ..., 3] = 1
+            break
+        i += 1
+    ref.close()
+    assert steps == nsteps
+    assert np.array_equal(have, exp_have)
+    assert vs.vsc_vs_test_flow_runs() - runs0 == 2 * flow_batches   # two directions per flow batch
+    for t in range(T):
+        if exp_have[t]:
+            assert np.array_equal(outs[t], exp[t]), t
+    if batch == 1 and scale == 1:   # and against the oracle (first three steps)
+        of = [O.rgba8_to_f32x3(x) for x in o8]
+        pf = [O.rgba8_to_f32x3(x) for x in p8]
+        last = pf[2]
+        for step_i, (a, b, c, f1, f2) in enumerate(ora[:3]):
+            last, rgba = O.do_one_step(of[a], of[b], of[c], pf[a], pf[b], pf[c], last, f1.cpu().numpy(), f2.cpu().numpy())
+            d = np.abs(outs[step_i + 1].astype(np.int32) - rgba.astype(np.int32))
+            assert d.max() <= 1, (step_i, d.max())

@@ -136,10 +136,10 @@ def test_stage_a_fused_equals_unfused(V, O, dev, W, H, fc):
     assert torch.equal(aP2, aP) and torch.equal(wt2, wt)
 
 
-def _oracle_sequence(O, o8, p8, ff, fb, steps, params=None):
+def _oracle_sequence(O, o8, p8, ff, fb, steps, params=None, batch=1):
     of = [O.rgba8_to_f32x3(x) for x in o8]
     pf = [O.rgba8_to_f32x3(x) for x in p8]
-    last = pf[2]
+    last = pf[1 + batch]   # lastStabilizedFrame <- the last of the 2k + batchSize preloaded frames (videostabilizer.cpp:152)
     outs = []
     for t in steps:
         co, rgba = O.do_one_step(of[t - 1], of[t], of[t + 1], pf[t - 1], pf[t], pf[t + 1], last, ff, fb, params)
@@ -180,6 +180,37 @@ def test_stabilizer_sequence_vs_oracle(V, O, dev, W, H, fc):
         got_f = st.last_output().cpu().numpy()
         ok, msg = near(got_f, ref[i][0], 3e-5)
         assert ok, f"step {t}: {msg}"
+        d = np.abs(out.astype(np.int32) - ref[i][1].astype(np.int32))
+        assert d.max() <= 1, f"step {t}: u8 max diff {d.max()}"
+        assert (d > 0).mean() < 0.01
+    st.close()
+
+
+@pytest.mark.parametrize("batch", [2, 4])
+def test_stabilizer_flow_batches_vs_oracle(V, O, dev, batch):
+    """`-b batchSize` (main.cpp:48-63): the window holds 2 + batchSize frames, the recurrence starts from the LAST
+    preloaded processed frame, steps consume window[0..2] (videostabilizer.cpp:136-153,167-190)."""
+    W, H, T = 64, 48, 9
+    o8, p8 = synth.frames(W, H, T, seed=79, mismatch=0.25)
+    ff, fb = synth.flows(W, H, 3)
+    steps = tuple(range(1, T - 1 - batch + 1))
+    ref = _oracle_sequence(O, o8, p8, ff, fb, steps, batch=batch)
+    st = V.Stabilizer(W, H, 3, batch_size=batch)
+    L = V.lib()
+    assert L.vsc_stabilizer_batch_size(st._h) == batch
+    dff, dfb = cu(ff, dev), cu(fb, dev)
+    torch.cuda.synchronize()
+    for t in range(2 + batch):
+        st.push_frame(o8[t], p8[t])
+    assert L.vsc_stabilizer_window_count(st._h) == 2 + batch
+    with pytest.raises(V.VscError):   # the window is full
+        st.push_frame(o8[0], p8[0])
+    for i, t in enumerate(steps):
+        out = np.zeros((H, W, 4), np.uint8)
+        st.step(dff, dfb, out)
+        if t + 1 + batch < T:
+            st.push_frame(o8[t + 1 + batch], p8[t + 1 + batch])
+        st.sync()
         d = np.abs(out.astype(np.int32) - ref[i][1].astype(np.int32))
         assert d.max() <= 1, f"step {t}: u8 max diff {d.max()}"
         assert (d > 0).mean() < 0.01

@@ -25,7 +25,8 @@
 
 namespace {
 
-constexpr int kSlots = 4;
+constexpr int kMaxBatch = 16;                 // flow batch sizes 1..16 (main.cpp:48-63: -b)
+constexpr int kMaxSlots = 2 + kMaxBatch + 1;  // window of 2k + batchSize frames (k = 1) + the slot being filled
 
 struct Pending {
     const uint8_t* src = nullptr;  // pinned result
@@ -37,19 +38,20 @@ struct Pending {
 
 struct vsc_stabilizer {
     int W = 0, H = 0, flowC = 3, device = 0;
+    int batch = 1, wcap = 3, nslots = 4;   // flow batch size, window capacity 2k + batch, ring slots wcap + 1
     size_t P = 0, n = 0;
     vsc_hyper_params hp{};
     cudaStream_t compute = nullptr, copy = nullptr, d2h = nullptr;
 
     // window ring
-    float* orig[kSlots] = {};
-    float* proc[kSlots] = {};
-    uint8_t* stage_dev[kSlots][2] = {};
-    uint8_t* stage_pin[kSlots][2] = {};
-    cudaEvent_t slot_ready[kSlots] = {};   // copy stream: upload + conversion of the slot finished
-    cudaEvent_t slot_h2d[kSlots] = {};     // copy stream: H2D from the slot's pinned staging finished
-    cudaEvent_t slot_released[kSlots] = {};  // compute stream: last step reading the slot finished
-    bool slot_used[kSlots] = {};
+    float* orig[kMaxSlots] = {};
+    float* proc[kMaxSlots] = {};
+    uint8_t* stage_dev[kMaxSlots][2] = {};
+    uint8_t* stage_pin[kMaxSlots][2] = {};
+    cudaEvent_t slot_ready[kMaxSlots] = {};   // copy stream: upload + conversion of the slot finished
+    cudaEvent_t slot_h2d[kMaxSlots] = {};     // copy stream: H2D from the slot's pinned staging finished
+    cudaEvent_t slot_released[kMaxSlots] = {};  // compute stream: last step reading the slot finished
+    bool slot_used[kMaxSlots] = {};
     int head = 0, count = 0;
     long long pushed = 0;
 
@@ -135,13 +137,13 @@ int ensure_workspace(vsc_stabilizer* s, int levels)
 
 int do_step(vsc_stabilizer* s, const float* flowFwd, const float* flowBwd, uint8_t* out_host)
 {
-    if (s->count != 3)
+    if (s->count < 3)
         return VSC_E_STATE;
     const vsc_hyper_params c = s->hp;  // snapshot once per frame (videostabilizer.cpp:192)
     int rc = ensure_workspace(s, c.pyramidLevels);
     if (rc)
         return rc;
-    const int s0 = s->head, s1 = (s->head + 1) % kSlots, s2 = (s->head + 2) % kSlots;
+    const int s0 = s->head, s1 = (s->head + 1) % s->nslots, s2 = (s->head + 2) % s->nslots;
     for (int k : {s0, s1, s2})
         if ((rc = cu(cudaStreamWaitEvent(s->compute, s->slot_ready[k], 0))))
             return rc;
@@ -183,7 +185,7 @@ int do_step(vsc_stabilizer* s, const float* flowFwd, const float* flowBwd, uint8
     for (int k : {s0, s1, s2})
         cudaEventRecord(s->slot_released[k], s->compute);
     s->head = s1;
-    s->count = 2;
+    s->count -= 1;
     return cu(cudaGetLastError());
 }
 
@@ -191,7 +193,16 @@ int do_step(vsc_stabilizer* s, const float* flowFwd, const float* flowBwd, uint8
 
 extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flow_channels)
 {
-    if (!out || W < 2 || H < 2 || H > 65535 || (flow_channels != 2 && flow_channels != 3))
+    return vsc_stabilizer_create_batched(out, W, H, flow_channels, 1);
+}
+
+extern "C" int vsc_stabilizer_batch_size(const vsc_stabilizer* s) { return s ? s->batch : 0; }
+extern "C" int vsc_stabilizer_window_count(const vsc_stabilizer* s) { return s ? s->count : 0; }
+
+extern "C" int vsc_stabilizer_create_batched(vsc_stabilizer** out, int W, int H, int flow_channels, int batchSize)
+{
+    if (!out || W < 2 || H < 2 || H > 65535 || (flow_channels != 2 && flow_channels != 3) || batchSize < 1
+        || batchSize > kMaxBatch)
         return VSC_E_INVALID;
     *out = nullptr;
     vsc_stabilizer* s = new (std::nothrow) vsc_stabilizer;
@@ -200,6 +211,9 @@ extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flo
     s->W = W;
     s->H = H;
     s->flowC = flow_channels;
+    s->batch = batchSize;
+    s->wcap = 2 + batchSize;
+    s->nslots = s->wcap + 1;
     s->P = static_cast<size_t>(W) * H;
     s->n = s->P * 3;
     vsc_hyper_params_default(&s->hp);
@@ -226,7 +240,7 @@ extern "C" int vsc_stabilizer_create(vsc_stabilizer** out, int W, int H, int flo
     if (!rc) rc = cu(cudaStreamCreateWithPriority(&s->compute, cudaStreamNonBlocking, prio_hi));
     if (!rc) rc = cu(cudaStreamCreateWithPriority(&s->copy, cudaStreamNonBlocking, prio_lo));
     if (!rc) rc = cu(cudaStreamCreateWithPriority(&s->d2h, cudaStreamNonBlocking, prio_lo));
-    for (int k = 0; k < kSlots; ++k) {
+    for (int k = 0; k < s->nslots; ++k) {
         dmalloc(reinterpret_cast<void**>(&s->orig[k]), fb);
         dmalloc(reinterpret_cast<void**>(&s->proc[k]), fb);
         for (int i = 0; i < 2; ++i) {
@@ -267,7 +281,7 @@ extern "C" void vsc_stabilizer_destroy(vsc_stabilizer* s)
     if (s->compute) cudaStreamSynchronize(s->compute);
     if (s->copy) cudaStreamSynchronize(s->copy);
     if (s->d2h) cudaStreamSynchronize(s->d2h);
-    for (int k = 0; k < kSlots; ++k) {
+    for (int k = 0; k < kMaxSlots; ++k) {
         cudaFree(s->orig[k]);
         cudaFree(s->proc[k]);
         for (int i = 0; i < 2; ++i) {
@@ -313,9 +327,9 @@ extern "C" int vsc_stabilizer_push_frame(vsc_stabilizer* s, const uint8_t* orig_
 {
     if (!s || !orig_rgba_host || !proc_rgba_host)
         return VSC_E_INVALID;
-    if (s->count >= 3)
+    if (s->count >= s->wcap)
         return VSC_E_STATE;  // the window is full: call vsc_stabilizer_step first
-    const int k = (s->head + s->count) % kSlots;
+    const int k = (s->head + s->count) % s->nslots;
     const size_t bytes = s->P * 4;
     int rc;
     // the slot may still be read by an in-flight step (it was window[0] two steps ago)
@@ -339,8 +353,9 @@ extern "C" int vsc_stabilizer_push_frame(vsc_stabilizer* s, const uint8_t* orig_
         if ((rc = vsc_rgba8_to_f32x3(s->stage_dev[k][i], dst[i], s->W, s->H, s->copy)))
             return rc;
     s->pushed += 1;
-    if (s->pushed == 3) {
-        // preloadProcessedFrames: lastStabilizedFrame <- processedFrames.back() (videostabilizer.cpp:152).  The
+    if (s->pushed == s->wcap) {
+        // preloadProcessedFrames: lastStabilizedFrame <- processedFrames.back() (videostabilizer.cpp:152), the LAST of
+        // the 2k + batchSize preloaded frames.  The
         // compute stream may still own lastStab only after a step, and none has run since create/reset.
         if ((rc = cu(cudaMemcpyAsync(s->lastStab, s->proc[k], s->n * sizeof(float), cudaMemcpyDeviceToDevice,
                  s->copy))))
@@ -365,7 +380,7 @@ extern "C" int vsc_stabilizer_step_lowres_flow(vsc_stabilizer* s, const float* f
 {
     if (!s || !flowFwd_dev || !flowBwd_dev || flowW <= 0 || flowH <= 0)
         return VSC_E_INVALID;
-    if (s->count != 3)
+    if (s->count < 3)
         return VSC_E_STATE;
     if (flowW == s->W && flowH == s->H)
         return do_step(s, flowFwd_dev, flowBwd_dev, out_rgba_host);
@@ -384,7 +399,7 @@ extern "C" int vsc_stabilizer_step_host_flow(vsc_stabilizer* s, const float* flo
 {
     if (!s || !flowFwd_host || !flowBwd_host || flowW <= 0 || flowH <= 0 || flowW > s->W || flowH > s->H)
         return VSC_E_INVALID;
-    if (s->count != 3)
+    if (s->count < 3)
         return VSC_E_STATE;
     const size_t bytes = static_cast<size_t>(flowW) * flowH * s->flowC * sizeof(float);
     int rc;
@@ -514,7 +529,7 @@ extern "C" int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flo
 {
     if (!s || !flow_dir || s->flowC != 2)
         return VSC_E_INVALID;
-    if (s->count != 3)
+    if (s->count < 3)
         return VSC_E_STATE;
     int rc = ensure_file_buffers(s);
     if (rc)
@@ -541,11 +556,11 @@ extern "C" int vsc_stabilizer_step_flow_files(vsc_stabilizer* s, const char* flo
 
 extern "C" int vsc_stabilizer_flow_input(vsc_stabilizer* s, int window_index, uint8_t* dst_dev, int netW, int netH)
 {
-    if (!s || !dst_dev || window_index < 0 || window_index > 2 || netW <= 0 || netH <= 0)
+    if (!s || !dst_dev || window_index < 0 || window_index >= s->wcap || netW <= 0 || netH <= 0)
         return VSC_E_INVALID;
-    if (s->count != 3)
+    if (window_index >= s->count)
         return VSC_E_STATE;
-    const int k = (s->head + window_index) % kSlots;
+    const int k = (s->head + window_index) % s->nslots;
     int rc = cu(cudaStreamWaitEvent(s->compute, s->slot_ready[k], 0));
     if (rc)
         return rc;
@@ -574,7 +589,7 @@ extern "C" int vsc_stabilizer_wait_uploads(vsc_stabilizer* s)
         return VSC_E_INVALID;
     // every H2D goes through the copy stream; the events below are recorded right behind the copies
     int rc = VSC_OK;
-    for (int k = 0; k < kSlots && !rc; ++k)
+    for (int k = 0; k < s->nslots && !rc; ++k)
         if (s->slot_used[k])
             rc = cu(cudaEventSynchronize(s->slot_h2d[k]));
     if (!rc && s->flow_used)
@@ -602,7 +617,7 @@ extern "C" int vsc_stabilizer_reset(vsc_stabilizer* s)
     s->head = 0;
     s->count = 0;
     s->pushed = 0;
-    for (int k = 0; k < kSlots; ++k)
+    for (int k = 0; k < s->nslots; ++k)
         s->slot_used[k] = false;
     return rc;
 }

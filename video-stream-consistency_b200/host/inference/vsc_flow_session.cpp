@@ -33,11 +33,13 @@ struct VscFlowSession::Binding {
 };
 
 VscFlowSession::VscFlowSession(Ort::Env& env, const std::string& model_path, int netW, int netH,
-    vsc_stabilizer* stabilizer, int device_id, bool batch_directions)
-    : netW_(netW), netH_(netH), batched_(batch_directions), st_(stabilizer)
+    vsc_stabilizer* stabilizer, int device_id, bool batch_directions, int batch_size)
+    : netW_(netW), netH_(netH), batched_(batch_directions), batch_size_(batch_size), st_(stabilizer)
 {
-    if (!stabilizer || netW <= 0 || netH <= 0)
+    if (!stabilizer || netW <= 0 || netH <= 0 || batch_size < 1 || (batch_directions && batch_size != 1))
         throw std::runtime_error("VscFlowSession: invalid arguments");
+    if (vsc_stabilizer_batch_size(stabilizer) != batch_size)
+        throw std::runtime_error("VscFlowSession: the stabilizer was created for another flow batch size");
 
     // InferenceModelVariant::createSession (:146-184), with the graph placed on the stabilizer's compute stream
     Ort::SessionOptions options;
@@ -56,7 +58,7 @@ VscFlowSession::VscFlowSession(Ort::Env& env, const std::string& model_path, int
     session_ = std::make_unique<Ort::Session>(env, model_path.c_str(), options);
 
     // CudaIO's allocations (CudaIO.cpp:37-52), once; zeroed like the reference's
-    const int64_t batch = batched_ ? 2 : 1;
+    const int64_t batch = batched_ ? 2 : batch_size_;
     const size_t frame_bytes = static_cast<size_t>(netW) * netH * 4;
     const size_t flow_bytes = static_cast<size_t>(netW) * netH * 3 * sizeof(float);
     for (int i = 0; i < 2; ++i) {
@@ -70,8 +72,9 @@ VscFlowSession::VscFlowSession(Ort::Env& env, const std::string& model_path, int
         flow_[1] = flow_[0] + static_cast<size_t>(netW) * netH * 3;
     } else {
         for (int i = 0; i < 2; ++i) {
-            cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&flow_[i]), flow_bytes), "Unable to allocate CUDA memory.");
-            cuda_or_throw(cudaMemset(flow_[i], 0, flow_bytes), "Unable to zero out CUDA memory.");
+            cuda_or_throw(cudaMalloc(reinterpret_cast<void**>(&flow_[i]), batch * flow_bytes),
+                "Unable to allocate CUDA memory.");
+            cuda_or_throw(cudaMemset(flow_[i], 0, batch * flow_bytes), "Unable to zero out CUDA memory.");
         }
     }
 
@@ -120,8 +123,13 @@ const float* VscFlowSession::run(int indexFirst, int indexSecond, int slot)
     if (slot < 0 || slot > 1)
         throw std::runtime_error("VscFlowSession::run: slot must be 0 or 1");
     // cpyNImagesToBuffer + QImage::scaled + CudaIO::setData (flowmodel.cpp:126-144) on the device
-    vsc_or_throw(vsc_stabilizer_flow_input(st_, indexFirst, frame_[slot], netW_, netH_), "flow input frame1");
-    vsc_or_throw(vsc_stabilizer_flow_input(st_, indexSecond, frame_[1 - slot], netW_, netH_), "flow input frame2");
+    const size_t frame_bytes = static_cast<size_t>(netW_) * netH_ * 4;
+    for (int b = 0; b < batch_size_; ++b) {
+        vsc_or_throw(vsc_stabilizer_flow_input(st_, indexFirst + b, frame_[slot] + b * frame_bytes, netW_, netH_),
+            "flow input frame1");
+        vsc_or_throw(vsc_stabilizer_flow_input(st_, indexSecond + b, frame_[1 - slot] + b * frame_bytes, netW_, netH_),
+            "flow input frame2");
+    }
     session_->Run(run_options_, bind_[slot]->io);
     return flow_[slot];
 }
@@ -143,8 +151,14 @@ void VscFlowSession::stabilizeCurrentFrame(uint8_t* out_rgba_host)
             "stabilizer step");
         return;
     }
-    const float* fwd = run(1, 2, 0);                 // videostabilizer.cpp:271
-    session_->Run(run_options_, bind_[1]->io);       // :272, run(2, 1): the same two frames, bound swapped
-    const float* bwd = flow_[1];
+    // every batch_size frames (videostabilizer.cpp:269): both directions for the whole batch
+    if (step_in_batch_ == 0) {
+        run(1, 2, 0);                                // :271
+        session_->Run(run_options_, bind_[1]->io);   // :272, run(2, 1): the same frames, bound swapped
+    }
+    const size_t flow_elems = static_cast<size_t>(netW_) * netH_ * 3;
+    const float* fwd = flow_[0] + step_in_batch_ * flow_elems;   // flowResultsFwd[batchIdx] (:176-179)
+    const float* bwd = flow_[1] + step_in_batch_ * flow_elems;
+    step_in_batch_ = (step_in_batch_ + 1) % batch_size_;
     vsc_or_throw(vsc_stabilizer_step_lowres_flow(st_, fwd, bwd, netW_, netH_, out_rgba_host), "stabilizer step");
 }

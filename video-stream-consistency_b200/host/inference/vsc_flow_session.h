@@ -33,8 +33,13 @@ public:
     // (profiles/time_ops_batched.py: 88 -> 72 us of custom-op GPU time per frame at 1080p/2, 587 -> 515 us for the
     // dense model at 4K).  The model must accept a batch dimension of 2 (the reference feeds [batchSize, H, W, 4],
     // flowmodel.cpp:62-70).
+    // batch_size (the CLI's `-b`, main.cpp:48-63; must equal the stabilizer's, vsc_stabilizer_create_batched): the
+    // session's tensors are [batch_size, netH, netW, 4] / [batch_size, netH, netW, 3] and the graph runs once per
+    // direction every batch_size frames -- on window frames 1..batch_size against 2..batch_size+1
+    // (videostabilizer.cpp:269-273, flowmodel.cpp:137-143) -- while the frames in between only index into the two
+    // flow batches (:176-179).  Not combinable with batch_directions.
     VscFlowSession(Ort::Env& env, const std::string& model_path, int netW, int netH, vsc_stabilizer* stabilizer,
-        int device_id = 0, bool batch_directions = false);
+        int device_id = 0, bool batch_directions = false, int batch_size = 1);
     ~VscFlowSession();
     VscFlowSession(const VscFlowSession&) = delete;
     VscFlowSession& operator=(const VscFlowSession&) = delete;
@@ -43,7 +48,8 @@ public:
     // (0 = previous, 1 = current, 2 = next), enqueued on the compute stream; the result lands in output slot
     // `slot` (0 or 1: forward / backward, so that both directions of a frame can be pending).  Returns the device
     // pointer of the [netH, netW, 3] float flow; valid until the next run into the same slot.  Not available on a
-    // session created with batch_directions (throws).
+    // session created with batch_directions (throws).  With batch_size > 1 the call fills the whole batch (frames
+    // indexFirst + b / indexSecond + b) and returns the [batch_size, netH, netW, 3] result.
     const float* run(int indexFirst, int indexSecond, int slot);
 
     // retrieveOpticalFlow + doOneStep (videostabilizer.cpp:167-279): both directions, then the stabilization step
@@ -57,6 +63,7 @@ private:
     struct Binding;
     int netW_, netH_;
     bool batched_;
+    int batch_size_ = 1, step_in_batch_ = 0;
     vsc_stabilizer* st_;
     uint8_t* frame_[2] = {nullptr, nullptr};   // bound inputs ([1,H,W,4] each; batched: [2,H,W,4] each)
     float* flow_[2] = {nullptr, nullptr};      // bound outputs, one per slot (batched: flow_[1] = flow_[0] + H*W*3)

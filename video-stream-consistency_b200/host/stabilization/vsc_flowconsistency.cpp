@@ -27,6 +27,8 @@
 #include <iostream>
 #include <mutex>
 #include <stdexcept>
+#include <unordered_map>
+#include <vector>
 
 #include "vsc/vsc.h"
 
@@ -165,16 +167,81 @@ void perform_consistency(GPUImage&, GPUImage& processedPrev, GPUImage&, GPUImage
 }
 
 // ------------------------------------------------------------------------------ gpuimage.h
+// The application creates and destroys two GPUImages per frame (imageToGPU in loadFrame, pop_front in doOneStep,
+// stabilizestream.cpp:72-73, videostabilizer.cpp:248-250) plus temporaries in FlowModel::run: with cudaMalloc /
+// cudaFree underneath that is four driver calls with an implicit device synchronisation per frame.  Freed blocks are
+// kept in a small per-size cache instead (every GPUImage operation here is synchronous, so a block is idle when its
+// image dies); cudaMalloc is only reached when a size is seen for the first time.
+namespace {
+struct BlockCache {
+    static constexpr size_t kPerSize = 8;                 // blocks kept per byte size
+    static constexpr size_t kMaxBytes = size_t(3) << 30;   // and in total
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void*>> free_blocks;
+    size_t cached = 0;
+
+    void* get(size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = free_blocks.find(bytes);
+            if (it != free_blocks.end() && !it->second.empty()) {
+                void* p = it->second.back();
+                it->second.pop_back();
+                cached -= bytes;
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess)
+            return p;
+        (void)cudaGetLastError();
+        drop_all();   // out of memory: give the cached blocks back and try once more
+        if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess)
+            throw std::runtime_error("Unable to allocate CUDA memory.");
+        return p;
+    }
+    void put(void* p, size_t bytes)
+    {
+        if (!p)
+            return;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            std::vector<void*>& v = free_blocks[bytes];
+            if (v.size() < kPerSize && cached + bytes <= kMaxBytes) {
+                v.push_back(p);
+                cached += bytes;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void drop_all()
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& kv : free_blocks)
+            for (void* p : kv.second)
+                cudaFree(p);
+        free_blocks.clear();
+        cached = 0;
+    }
+};
+BlockCache& blocks()
+{
+    static BlockCache* c = new BlockCache;   // never destroyed: images with static storage may die after it would
+    return *c;
+}
+size_t image_bytes(int w, int h, int c) { return static_cast<size_t>(w) * h * c * sizeof(float); }
+}  // namespace
+
 GPUImage::GPUImage(int width, int height, int channels) : width(width), height(height), channels(channels)
 {
-    const size_t nelems = static_cast<size_t>(width) * height * channels;
-    if (cudaMalloc(reinterpret_cast<void**>(&data), nelems * sizeof(float)) != cudaSuccess)
-        throw std::runtime_error("Unable to allocate CUDA memory.");
+    data = static_cast<float*>(blocks().get(image_bytes(width, height, channels)));
 }
 
 GPUImage::GPUImage(const GPUImage& other) : GPUImage(other.width, other.height, other.channels) { copyFrom(other); }
 
-GPUImage::~GPUImage() { cudaFree(data); }
+GPUImage::~GPUImage() { blocks().put(data, image_bytes(width, height, channels)); }
 
 void GPUImage::copyFrom(const GPUImage& other)
 {

@@ -241,13 +241,14 @@ class Stabilizer:
     """One video stream on the current CUDA device: VideoStabilizer's preload + doOneStep recurrence
     (videostabilizer.cpp:136-153,167-265) on top of vsc_stabilizer_*."""
 
-    def __init__(self, width: int, height: int, flow_channels: int = 3):
+    def __init__(self, width: int, height: int, flow_channels: int = 3, batch_size: int = 1):
         self._h = C.c_void_p(0)
         if not torch.cuda.is_available():
             raise VscError("Stabilizer needs a CUDA device (no CPU fallback exists)")
         self.W, self.H, self.flow_channels = int(width), int(height), int(flow_channels)
+        self.batch_size = int(batch_size)   # `-b`: the window holds 2 + batch_size frames (videostabilizer.cpp:136-153)
         self._h = C.c_void_p(0)
-        check(lib().vsc_stabilizer_create(C.byref(self._h), self.W, self.H, self.flow_channels))
+        check(lib().vsc_stabilizer_create_batched(C.byref(self._h), self.W, self.H, self.flow_channels, self.batch_size))
         self._inflight = []     # tensors / host buffers the asynchronous steps still use (released by sync())
         self._xstream = None
 

@@ -46,6 +46,9 @@ PROTOTYPES = {
     "vsc_frame_stabilize_workspace_bytes": (_sz, [_i, _i, _i]),
     "vsc_frame_stabilize": (_i, [_p] * 9 + [_i, _p, _p, _i, _i, _p, _sz, _p]),
     "vsc_stabilizer_create": (_i, [_p, _i, _i, _i]),
+    "vsc_stabilizer_create_batched": (_i, [_p, _i, _i, _i, _i]),
+    "vsc_stabilizer_batch_size": (_i, [_p]),
+    "vsc_stabilizer_window_count": (_i, [_p]),
     "vsc_stabilizer_destroy": (None, [_p]),
     "vsc_stabilizer_hyper_params": (_p, [_p]),
     "vsc_stabilizer_push_frame": (_i, [_p, _p, _p]),
