@@ -310,6 +310,10 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
             // software pipeline: the next 128-bit in2 load is in flight while the current one feeds 16 FMAs
             float4 bn = *reinterpret_cast<const float4*>(sB);
             float4 an = *reinterpret_cast<const float4*>(sA);
+            // (rolled: unrolling the 8 channels of the chunk 2x / 4x / 8x turns every offset into an immediate and removes
+            // the compares and branches -- 36 % of the issued instructions -- and changes nothing: 96-100 us at
+            // 32x544x960 either way, profiles/r2_correlation_unroll_events.txt.  ncu, r2_correlation_ncu.txt: issue 64 %,
+            // FMA pipe 45 %, shared-memory wavefronts 57 %, stalls short_scoreboard / wait / long_scoreboard)
 #pragma unroll 1
             for (int c = 0; c < kKC; ++c) {
                 const float av[4] = {an.x, an.y, an.z, an.w};
