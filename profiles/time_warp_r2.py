@@ -57,6 +57,21 @@ for (C, H, W) in SHAPES:
     print(f"C{C} {H}x{W}: {nbytes / 1e6:.1f} MB; device copy of the tensor {tc:.1f} us ({4 * H * W * 2 * C / tc / 1e3 / PEAK:.2f})")
     flows = (("bench-smooth", torch.from_numpy(synth.op_flow_smooth(1, H, W, 3)).to(dev)),
              ("random-s2", 2.0 * torch.randn((1, 2, H, W), device=dev, generator=g)))
+    # the bench's method for the default selection: 20 launches back to back over two tensor sets
+    sets = [(torch.randn((1, C, H, W), device=dev, generator=g), flows[0][1], torch.empty((1, C, H, W), device=dev))
+            for _ in range(2)]
+    for s_ in sets:
+        V.warp(s_[0], s_[1], out=s_[2])
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for i in range(20):
+        s_ = sets[i & 1]
+        V.warp(s_[0], s_[1], out=s_[2])
+    eb.record()
+    torch.cuda.synchronize()
+    tb = ea.elapsed_time(eb) / 20 * 1e3
+    print(f"   default selection, back to back on the bench's smooth flow: {tb:.1f} us ({nbytes / tb / 1e3 / PEAK:.3f})")
     for name, fl in flows:
         row = []
         ref = None

@@ -30,7 +30,10 @@ namespace {
 constexpr int kTileW = 64, kTileH = 8;           // output pixels per CTA
 constexpr int kThreads = 256;                    // two pixels per thread: rows ty and ty + 4
 constexpr int kBX = 72, kBY = 12;                // staged box (floats x rows): 64 + 1 (xR) + 3 (alignment) + 4 slack
-constexpr int kG = 4;                            // channels per stage
+#ifndef VSC_WARP_G
+#define VSC_WARP_G 4
+#endif
+constexpr int kG = VSC_WARP_G;                   // channels per stage
 #ifndef VSC_WARP_STAGES
 #define VSC_WARP_STAGES 3
 #endif
