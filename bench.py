@@ -456,7 +456,7 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
 
     # ---------------- roofline of the dominant kernel: the level-0 solver ----------------
     # marginal time of n sweeps = t(2n) - t(n), CUDA events on the launching stream.  In the default mode the
-    # sweeps run as temporally blocked passes (solver_stream_kernel<T>, T sweeps per launch); the unblocked
+    # sweeps run as temporally blocked passes (solver_rolled_kernel<T>, T sweeps per launch); the unblocked
     # sweep kernel is timed beside it (mode 1).  Algorithmic bytes: 72 B/pixel/sweep.
     def time_solve(iters):
         x = d_p[1].clone()
@@ -550,7 +550,7 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
                              "gflops": 2.0 * 81 * Cc * h * w / (ms * 1e-3) / 1e9})
 
     dram_frac = (traffic / (pass_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None
-    roofline = {"kernel": f"solver_stream_kernel<{T_main}> (level 0, {T_main} Jacobi sweeps per launch, on-chip)",
+    roofline = {"kernel": f"solver_rolled_kernel<{T_main}> (level 0, {T_main} Jacobi sweeps per launch, on-chip)",
                 # what limits the kernel per ncu (profiles/): instruction issue + shared-memory wavefronts; the HBM
                 # roofline in ALGORITHMIC bytes is kept as the contract's yardstick, dram_frac is the real DRAM load
                 "bound": "issue/smem", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -179,9 +179,9 @@ def test_warp_kernels_agree(V, dev):
     # (the shapes with W % 4 == 0, W >= 72, H >= 12 run the TMA-staged kernel in mode 4: smooth flow -> staged tiles,
     # random flow -> its gather path, and (50, 148) / (33, 200) have partial tiles at the right and bottom edges)
     for (N, C, H, W) in ((2, 12, 67, 131), (1, 7, 5, 3), (1, 4, 2, 2), (1, 33, 40, 64), (2, 9, 41, 100), (1, 5, 70, 33),
-                         (2, 13, 50, 148), (1, 8, 33, 200), (1, 32, 136, 240), (2, 6, 64, 128)):
+                         (2, 13, 50, 148), (1, 8, 33, 200), (1, 32, 136, 240), (2, 6, 64, 128), (1, 12, 544, 960), (2, 7, 300, 480)):
         x = torch.randn((N, C, H, W), device=dev, generator=g)
-        if (H, W) in ((41, 100), (70, 33), (50, 148), (136, 240)):
+        if (H, W) in ((41, 100), (70, 33), (50, 148), (136, 240), (544, 960)):
             # smooth flow: neighbouring lanes sample neighbouring taps (the shuffle kernel's fast path), with a few
             # NaN / huge displacements so that live and dead lanes alternate inside a warp
             f = torch.from_numpy(synth.op_flow_smooth(N, H, W, 3, amp=3.0, noise=0.05)).to(dev)
