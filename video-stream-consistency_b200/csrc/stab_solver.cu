@@ -293,7 +293,7 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 extern "C" int vsc_set_solver_mode(int mode)
 {
     const int lo = mode & 0xFFFF;
-    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0x4800) || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2 || (mode >> 28))
+    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0x0800) || (lo & 0xC000) == 0xC000 || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2 || (mode >> 28))
         return VSC_E_INVALID;
     g_solver_mode = lo & 0xF;
     g_stream_pair = (lo & 0x10) == 0;
@@ -302,7 +302,7 @@ extern "C" int vsc_set_solver_mode(int mode)
     g_pdl = (lo & 0x80) == 0;
     g_stream_tmain = ((lo >> 12) & 3) == 0 ? 0 : 6 + 2 * ((lo >> 12) & 3);
     g_stream_band = (lo >> 8) & 7;
-    g_stream_rolled = (lo & 0x8000) ? 0 : 1;
+    g_stream_rolled = (lo & 0x8000) ? 0 : (lo & 0x4000) ? 2 : 1;
     g_stream_edge_top = ((mode >> 16) & 0x3F) - 1;   // 0 = default
     g_stream_edge_bot = ((mode >> 22) & 0x3F) - 1;
     return VSC_OK;

@@ -40,7 +40,7 @@ __host__ __device__ constexpr int rolled_halo(int T) { return (3 * T + 3) / 4 * 
 extern bool g_stream_pair;          // stab_solver_stream.cu: neighbour-pair named barriers (default) or CTA barrier
 extern bool g_stream_coop;          // false: per-thread 4-byte staging requested -> stab_solver_stream.cu
 extern int g_stream_band;           // 0 = cost model; 1..4 force a band width (512, 448, 384, 256)
-int g_stream_rolled = 1;            // 0: never use this kernel (vsc_set_solver_mode | 0x8000)
+int g_stream_rolled = 1;            // 0: never use this kernel (vsc_set_solver_mode | 0x8000), 1: auto, 2: always (| 0x4000)
 int g_stream_edge_top = -1;         // rows by which the first / last row chunk is shorter than the others (-1: default)
 int g_stream_edge_bot = -1;
 
@@ -337,6 +337,11 @@ bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const flo
     if ((3LL * W) % 4 != 0 || !aligned16(coefA) || !aligned16(coefB) || !aligned16(u_src) || !aligned16(o_src))
         return false;
     if (3LL * W * (static_cast<long long>(H) + 64) >= 0x7fffffffLL)   // 32-bit element offsets in the kernel
+        return false;
+    // 4K-class images: a CTA runs 570 steps per pass, the fully unrolled loop stays resident and its 8 % fewer
+    // instructions win (201.6 vs 205.1 us per pass, profiles/r2_solver_sweep_rolled.txt); g_stream_rolled == 2 forces
+    // this kernel regardless (tests)
+    if (g_stream_rolled == 1 && T == 10 && static_cast<long long>(W) * H >= 4000000LL)
         return false;
     switch (T) {
         case 10: *rc = launch_rolled_best<10>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
