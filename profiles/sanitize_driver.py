@@ -38,13 +38,22 @@ for (N, C, H, W) in ((1, 12, 24, 128), (2, 9, 17, 40), (1, 20, 9, 15), (1, 5, 7,
         V.check(L.vsc_set_warp_mode(mode))
         V.warp(a, f)
     L.vsc_set_warp_mode(0)
+# TMA-staged Warp (round 2): staged tiles (smooth flow), its gather path (scattered flow), partial tiles, channel chunks
+for (N, C, H, W) in ((1, 12, 40, 148), (2, 9, 33, 200)):
+    a = torch.randn((N, C, H, W), device=dev, generator=g)
+    for f in (torch.from_numpy(synth.op_flow_smooth(N, H, W, 3)).to(dev), 6.0 * torch.randn((N, 2, H, W), device=dev, generator=g)):
+        for mode in (4, 4 | (2 << 4)):
+            V.check(L.vsc_set_warp_mode(mode))
+            V.warp(a, f)
+    L.vsc_set_warp_mode(0)
 
 # solver: unblocked, blocked (pair barriers, CTA barrier, private staging, no PDL, 8 and 10 sweeps), odd widths
 for (W, H) in ((160, 96), (45, 37), (400, 64)):
     pr = torch.rand((H, W, 3), device=dev, generator=g)
     tg = torch.rand((H, W, 3), device=dev, generator=g)
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
-    for mode in (1, 2, 0x12, 0x22, 0x82, 0x1002, 0x2002, 0x2022):
+    # (round 2: the default is the 4-step loop; 0x8000 = the fully unrolled form, 0x4000 forces the loop, edge fields)
+    for mode in (1, 2, 0x12, 0x22, 0x82, 0x1002, 0x2002, 0x2022, 0x8002, 0x8012, 0xA002, 0x6002, 2 | (17 << 16) | (11 << 22)):
         V.check(L.vsc_set_solver_mode(mode))
         for iters in (1, 9, 21):
             V.get_consist_out(pr, tg, wt, iters, 0.15, 0.15, pr.clone())
