@@ -223,8 +223,10 @@ static SweepPlan plan_sweeps(int W, int H, int iters)
 
 // `iters` sweeps starting from the state in x (momentum in b.u, zeroed by the prepare kernel); the result
 // lands in x if plan.flips() is even, else in y
+// u_zero: b.u has NOT been zeroed; the first blocked pass is told so (null momentum input: it stages zeros instead
+// of reading 12 bytes per pixel of them), and only a solve without any blocked pass zeroes the image here
 static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, int iters, float step, float mom,
-    cudaStream_t st, float** result)
+    cudaStream_t st, float** result, bool u_zero = false)
 {
     const SweepPlan plan = plan_sweeps(W, H, iters);
     float* src = x;
@@ -233,10 +235,17 @@ static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, i
     float* ud = b.u2;
     int rc = VSC_OK;
     const int npass = plan.n8 + (plan.tail ? 1 : 0);
+    if (u_zero && npass == 0 && iters > 0) {
+        const cudaError_t e = cudaMemsetAsync(b.u, 0, static_cast<size_t>(W) * H * 3 * sizeof(float), st);
+        if (e != cudaSuccess)
+            return static_cast<int>(e);
+        u_zero = false;
+    }
     for (int k = 0; k < npass && rc == VSC_OK; ++k) {
         const int T = k < plan.n8 ? plan.tmain : plan.tail;
-        if (!solver_rolled_pass(T, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st, &rc))
-            rc = solver_stream_pass(T, b.coefA, b.coefB, us, ud, src, dst, W, H, step, mom, st);
+        const float* uin = (u_zero && k == 0) ? nullptr : us;
+        if (!solver_rolled_pass(T, b.coefA, b.coefB, uin, ud, src, dst, W, H, step, mom, st, &rc))
+            rc = solver_stream_pass(T, b.coefA, b.coefB, uin, ud, src, dst, W, H, step, mom, st);
         float* t = src; src = dst; dst = t;
         t = us; us = ud; ud = t;
     }
@@ -418,8 +427,7 @@ static int frame_solve_impl(const float* procCur, const float* adapCmbPr, const 
             p->gamma, p->stepSize, sb[0].coefA, sb[0].coefB, const_cast<float*>(pr[1]), const_cast<float*>(tg[1]),
             const_cast<float*>(wt[1]), W, H, st);
         if (rc) return rc;
-        const cudaError_t e = cudaMemsetAsync(sb[0].u, 0, d.n[0] * sizeof(float), st);  // momentum starts at 0
-        if (e != cudaSuccess) return static_cast<int>(e);
+        // (momentum starts at 0: the level-0 solve below is told so instead of zeroing 12 bytes per pixel here)
     }
     // pyramid down (videostabilizer.cpp:210-216).  pyrConsisOut[0] is a copy of the processed frame (:209),
     // so its downsampled version equals pyrPr[j] -- computed once and copied.
@@ -456,7 +464,7 @@ static int frame_solve_impl(const float* procCur, const float* adapCmbPr, const 
             if (rc) return rc;
         }
         float* res = nullptr;
-        rc = run_sweeps(sb[j], x, y, d.w[j], d.h[j], iters, p->stepSize, p->momFac, st, &res);
+        rc = run_sweeps(sb[j], x, y, d.w[j], d.h[j], iters, p->stepSize, p->momFac, st, &res, stageA && j == 0);
         if (rc) return rc;
         coarse_result = res;  // == final_buf (also when iters == 0: x == final_buf since 0 is even)
     }

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
     const float* const my_src = arr == 0 ? o_src : arr == 1 ? u_src : arr == 2 ? coefA : coefB;
     int my_eoff = (r0 - T) * L + (chunk_ok ? gcol : 0);   // element offset of (next requested row, my chunk)
     const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + wcol));
-    const unsigned chunk_bytes = chunk_ok ? 16u : 0u;
+    // (u_src == nullptr: the momentum image is all zeros -- the first pass of a solve -- and is not read at all)
+    const unsigned chunk_bytes = (chunk_ok && my_src != nullptr) ? 16u : 0u;
     auto request = [&](int y, int slot, bool commit) {
         const unsigned n = (y >= 0 && y < H) ? chunk_bytes : 0u;
         const unsigned d = my_dst + static_cast<unsigned>(slot * SLOT * sizeof(float));
@@ -335,7 +336,7 @@ bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const flo
     if (!g_stream_rolled || !g_stream_coop)
         return false;
     if ((3LL * W) % 4 != 0 || !aligned16(coefA) || !aligned16(coefB) || !aligned16(u_src) || !aligned16(o_src))
-        return false;
+        return false;   // (a null u_src counts as aligned)
     if (3LL * W * (static_cast<long long>(H) + 64) >= 0x7fffffffLL)   // 32-bit element offsets in the kernel
         return false;
     // 4K-class images: a CTA runs 570 steps per pass, the fully unrolled loop stays resident and its 8 % fewer

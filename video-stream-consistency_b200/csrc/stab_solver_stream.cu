@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
         const unsigned n = (col_ok && y >= 0 && y < H) ? 4u : 0u;
         const unsigned d = stage_base + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(bo + off), "r"(n) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + BW * 4), "l"(bu + off), "r"(n) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + BW * 4), "l"(bu + off), "r"(bu ? n : 0u)
+                     : "memory");   // (u_src == nullptr: zero momentum, not read)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 2 * BW * 4), "l"(ba + off), "r"(n)
                      : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 3 * BW * 4), "l"(bb + off), "r"(n)
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(BW, 1) solver_stream_kernel(const float* __res
     // row of the NEXT request (PF-1 rows ahead of step s), first column of my chunk
     int my_eoff = (r0 - T + PF - 1) * L + (chunk_ok ? gcol : 0);
     const unsigned my_dst = static_cast<unsigned>(__cvta_generic_to_shared(stage + arr * BW + wcol));
-    const unsigned chunk_bytes = chunk_ok ? 16u : 0u;
+    const unsigned chunk_bytes = (chunk_ok && my_src != nullptr) ? 16u : 0u;   // (null u_src: zero momentum, not read)
     auto coop_copy = [&](const float* src, bool row_ok, int slot) {
         const unsigned n = row_ok ? chunk_bytes : 0u;   // src-size 0: zero fill, the source is not read
         const unsigned d = my_dst + static_cast<unsigned>(slot * 4 * BW * sizeof(float));
