@@ -146,8 +146,9 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  * blocked kernel (512, 448, 384, 256 floats) instead of the cost model; | 0x8000 = the fully unrolled form of the
  * blocked kernel (stab_solver_stream.cu) instead of the 4-step loop (stab_solver_rolled.cu; needs 16-byte aligned
  * rows; by default it takes every pass except the 10-sweep passes of images of 4 Mpx and more), | 0x4000 = the 4-step
- * loop for those too; | 0x0800 = a 2-sweep remainder after 8-sweep passes runs as its own pass (default: merged with the
- * last main pass into one 10-sweep pass); | ((a + 1) << 16) | ((b + 1) << 22), a, b in 0..62: the first / last row chunk of the 4-step-loop kernel is
+ * loop for those too; | 0x0800 = the sweeps are split into the fewest passes of nearly equal depth, odd depths 3..9
+ * included (75 = 3 x 10 + 5 x 9; default: 8- or 10-sweep passes, a 2-sweep remainder merged into the last pass, an odd
+ * sweep on its own: measured faster); | ((a + 1) << 16) | ((b + 1) << 22), a, b in 0..62: the first / last row chunk of the 4-step-loop kernel is
  * a / b rows shorter than the others (default 8 / 4).
  * Process-wide; meant for tests and benchmarks. */
 VSC_API int vsc_set_solver_mode(int mode);

@@ -182,41 +182,66 @@ extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of
 extern int g_stream_band, g_stream_edge_top, g_stream_edge_bot;
 bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
-int g_stream_tmain = 0;                     // sweeps per main blocked pass: 0 = chosen per solve, else 8 or 10
+int g_stream_tmain = 0;                     // deepest blocked pass: 0 = chosen per solve, else 8 or 10
 
-// how `iters` sweeps are executed: n8 passes of `tmain` sweeps, one pass of `tail` (even, < tmain) sweeps, `rest`
-// in {0,1} single unblocked sweeps (tmain = 8: 150 = 18x8 + 6, 75 = 9x8 + 2 + 1)
+// How `iters` sweeps are executed: n_hi blocked passes of t_hi sweeps, then n_lo passes of t_lo, then `rest` single
+// unblocked sweeps.  Every pass is exact Jacobi, so any partition gives the same result.
 struct SweepPlan {
-    int n8, tail, rest, tmain;
-    int flips() const { return n8 + (tail ? 1 : 0) + rest; }  // number of out-buffer ping-pongs
+    int n_hi, t_hi, n_lo, t_lo, rest;
+    int passes() const { return n_hi + n_lo; }
+    int flips() const { return n_hi + n_lo + rest; }  // number of out-buffer ping-pongs
+    int depth(int k) const { return k < n_hi ? t_hi : t_lo; }
 };
-bool g_plan_merge_tail = true;   // vsc_set_solver_mode(| 0x0800): keep the 2-sweep tail pass (A/B runs)
+bool g_plan_balanced = false;   // vsc_set_solver_mode(| 0x0800): passes of nearly equal depth, odd depths included
+bool solver_rolled_takes(int W, const void* a, const void* b, const void* c, const void* d);   // stab_solver_rolled.cu
 
-static SweepPlan plan_sweeps(int W, int H, int iters)
+// even_only: the passes will run in stab_solver_stream.cu (rows that are not 16-byte aligned, or by request), which
+// is built for depths 2, 4, 6, 8, 10 only
+static SweepPlan plan_sweeps(int W, int H, int iters, bool even_only)
 {
-    SweepPlan p{0, 0, iters, 8};
+    SweepPlan p{0, 0, 0, 0, iters};
     // tiny images: the 3T-step pipeline fill and the 6T-float band halo dominate -> plain sweeps
     const bool big = H >= 48 && 3 * W >= 384;
     // images beyond 2^31 floats: the blocked kernel addresses with 32-bit element offsets
     const bool fits32 = 3LL * W * (static_cast<long long>(H) + 64) < 0x7fffffffLL;
-    if (g_solver_mode == 1 || !fits32 || (g_solver_mode == 0 && !big))
-        return p;  // {0, 0, iters}
-    // 10-sweep passes pay off on large images only (a pass costs 1.15-1.22x an 8-sweep pass from 720p up, more below),
-    // and only if they save enough passes: 150 = 15 x 10 against 18 x 8 + 6
+    if (g_solver_mode == 1 || !fits32 || (g_solver_mode == 0 && !big) || iters < 2)
+        return p;  // plain sweeps only
+    if (g_plan_balanced && !even_only) {
+        // The fewest passes: ceil(iters / tmax) passes of nearly equal depth, odd depths included, no single sweeps
+        // (75 sweeps = 3 x 10 + 5 x 9, 150 = 15 x 10).  Bit-identical like every partition, and measured SLOWER than
+        // the default plan at 1080p (733 vs 741-746 frames/s sustained, profiles/r2_plan_balanced_ab.txt): passes of 9
+        // and 10 sweeps need the 384-float bands (168 registers), and at 960x540 the wider bands of the 8-sweep passes
+        // win back more than the two passes saved.  Kept as a tested option.
+        const int tmax = g_stream_tmain ? g_stream_tmain : (static_cast<long long>(W) * H >= 500000 ? 10 : 8);
+        const int npass = (iters + tmax - 1) / tmax;
+        const int base = iters / npass;
+        p.n_hi = iters % npass;
+        p.t_hi = base + 1;
+        p.n_lo = npass - p.n_hi;
+        p.t_lo = base;
+        p.rest = 0;
+        return p;
+    }
+    // main passes of 8 or 10 sweeps, one even tail pass, an odd sweep on its own.  10-sweep passes pay off on
+    // large images only (a pass costs 1.15-1.22x an 8-sweep pass from 720p up, more below), and only if they
+    // save enough passes: 150 = 15 x 10 against 18 x 8 + 6
+    int tmain = 8;
     auto passes = [&](int t) { return iters / t + (((iters % t) & ~1) ? 1 : 0); };
     const bool large = static_cast<long long>(W) * H >= 900000;
     if (g_stream_tmain == 10 || (g_stream_tmain == 0 && large && passes(10) * 121 < passes(8) * 100))
-        p.tmain = 10;
-    p.n8 = iters / p.tmain;
-    p.tail = (iters % p.tmain) & ~1;
+        tmain = 10;
+    p.n_hi = iters / tmain;
+    p.t_hi = tmain;
+    p.t_lo = (iters % tmain) & ~1;
+    p.n_lo = p.t_lo ? 1 : 0;
     p.rest = iters & 1;
     // A pass costs about 11 us + 1.3 us per sweep at 960x540 (pipeline fill, launch): a 2-sweep tail pass costs
     // two thirds of an 8-sweep one (17.8 vs 23.5 us, profiles/r2_launches_bench_default.txt).  8 + 2 = 10: the last
     // main pass takes the tail along as ONE 10-sweep pass (75 sweeps at level 1 = 8 x 8 + 10 + 1 instead of
     // 9 x 8 + 2 + 1).  Same sweeps, same results.
-    if (g_plan_merge_tail && p.tmain == 8 && p.tail == 2 && p.n8 >= 1) {
-        p.n8 -= 1;
-        p.tail = 10;
+    if (tmain == 8 && p.t_lo == 2 && p.n_hi >= 1) {
+        p.n_hi -= 1;
+        p.t_lo = 10;
     }
     return p;
 }
@@ -225,16 +250,21 @@ static SweepPlan plan_sweeps(int W, int H, int iters)
 // lands in x if plan.flips() is even, else in y
 // u_zero: b.u has NOT been zeroed; the first blocked pass is told so (null momentum input: it stages zeros instead
 // of reading 12 bytes per pixel of them), and only a solve without any blocked pass zeroes the image here
+static bool even_depths_only(const SolveBuffers& b, const float* x, const float* y, int W)
+{
+    return !solver_rolled_takes(W, b.coefA, b.coefB, b.u, b.u2) || !aligned16(x) || !aligned16(y);
+}
+
 static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, int iters, float step, float mom,
     cudaStream_t st, float** result, bool u_zero = false)
 {
-    const SweepPlan plan = plan_sweeps(W, H, iters);
+    const SweepPlan plan = plan_sweeps(W, H, iters, even_depths_only(b, x, y, W));
     float* src = x;
     float* dst = y;
     float* us = b.u;
     float* ud = b.u2;
     int rc = VSC_OK;
-    const int npass = plan.n8 + (plan.tail ? 1 : 0);
+    const int npass = plan.passes();
     if (u_zero && npass == 0 && iters > 0) {
         const cudaError_t e = cudaMemsetAsync(b.u, 0, static_cast<size_t>(W) * H * 3 * sizeof(float), st);
         if (e != cudaSuccess)
@@ -242,7 +272,7 @@ static int run_sweeps(const SolveBuffers& b, float* x, float* y, int W, int H, i
         u_zero = false;
     }
     for (int k = 0; k < npass && rc == VSC_OK; ++k) {
-        const int T = k < plan.n8 ? plan.tmain : plan.tail;
+        const int T = plan.depth(k);
         const float* uin = (u_zero && k == 0) ? nullptr : us;
         if (!solver_rolled_pass(T, b.coefA, b.coefB, uin, ud, src, dst, W, H, step, mom, st, &rc))
             rc = solver_stream_pass(T, b.coefA, b.coefB, uin, ud, src, dst, W, H, step, mom, st);
@@ -298,7 +328,8 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
     const size_t n = static_cast<size_t>(W) * H * 3;
     const SolveBuffers b = carve(workspace, n);
     // start in the buffer that makes the last sweep (or blocked pass) land in consisOut
-    const bool odd = (plan_sweeps(W, H, numIter).flips() & 1) != 0;
+    // (the plan depends on whether the 4-step-loop kernel can take the passes: 16-byte aligned rows and buffers)
+    const bool odd = (plan_sweeps(W, H, numIter, even_depths_only(b, consisOut, b.alt, W)).flips() & 1) != 0;
     int rc = launch_prepare(crntPr, prevStabWarp, consWt, b, odd ? consisOut : nullptr, odd ? b.alt : nullptr, W, H,
         stepSize, st);
     if (rc)
@@ -321,7 +352,7 @@ extern "C" int vsc_set_solver_mode(int mode)
     g_stream_tmain = ((lo >> 12) & 3) == 0 ? 0 : 6 + 2 * ((lo >> 12) & 3);
     g_stream_band = (lo >> 8) & 7;
     g_stream_rolled = (lo & 0x8000) ? 0 : (lo & 0x4000) ? 2 : 1;
-    g_plan_merge_tail = (lo & 0x0800) == 0;
+    g_plan_balanced = (lo & 0x0800) != 0;
     g_stream_edge_top = ((mode >> 16) & 0x3F) - 1;   // 0 = default
     g_stream_edge_bot = ((mode >> 22) & 0x3F) - 1;
     return VSC_OK;
@@ -444,7 +475,8 @@ static int frame_solve_impl(const float* procCur, const float* adapCmbPr, const 
     float* coarse_result = nullptr;
     for (int j = levels - 1; j >= 0; --j) {
         const int iters = p->numIter / (j + 1);
-        const bool odd = (plan_sweeps(d.w[j], d.h[j], iters).flips() & 1) != 0;
+        float* final_probe = (j == 0) ? consisOut : out[j];
+        const bool odd = (plan_sweeps(d.w[j], d.h[j], iters, even_depths_only(sb[j], final_probe, sb[j].alt, d.w[j])).flips() & 1) != 0;
         // x = buffer holding the initial state, y = the other one; the result lands in `final`
         float* final_buf = (j == 0) ? consisOut : out[j];
         float* x = odd ? sb[j].alt : final_buf;

@@ -37,6 +37,8 @@
 namespace vsc {
 
 __host__ __device__ constexpr int rolled_halo(int T) { return (3 * T + 3) / 4 * 4; }
+// staging ring depth (rows in flight from HBM): about 2T, a multiple of 4 (the slot base advances by 4 per group)
+__host__ __device__ constexpr int rolled_pf(int T) { return (2 * T + 3) / 4 * 4 < 8 ? 8 : (2 * T + 3) / 4 * 4; }
 extern bool g_stream_pair;          // stab_solver_stream.cu: neighbour-pair named barriers (default) or CTA barrier
 extern bool g_stream_coop;          // false: per-thread 4-byte staging requested -> stab_solver_stream.cu
 extern int g_stream_band;           // 0 = cost model; 1..4 force a band width (512, 448, 384, 256)
@@ -52,9 +54,9 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
 {
     constexpr int HALO = rolled_halo(T);
     constexpr int S = BW - 2 * HALO;   // columns stored per band
-    constexpr int PF = 2 * T;          // staging ring depth (rows in flight from HBM); a multiple of 4
+    constexpr int PF = rolled_pf(T);   // staging ring depth (rows in flight from HBM); a multiple of 4
     constexpr int NX = 2 * T + 4;      // coefficient window: rows s0-2T .. s0+3 of a group starting at step s0
-    static_assert(BW % 64 == 0 && PF % 4 == 0 && T % 2 == 0, "geometry");
+    static_assert(BW % 64 == 0 && PF % 4 == 0 && PF >= 8 && T >= 2, "geometry");
     extern __shared__ float smem_raw[];
     // exchange ring: T*4 rows of RW = BW + 8 floats; the 8 floats between two rows are never written, so the band's
     // first / last three threads read 0.0f for their out-of-band neighbours
@@ -264,7 +266,7 @@ template <int T, int BW, int SYNC>
 static int launch_rolled_impl(const RolledGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
-    constexpr int PF = 2 * T;
+    constexpr int PF = rolled_pf(T);
     const size_t smem = (static_cast<size_t>(T) * 4 * (BW + 8) + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static unsigned long long configured = 0;
     if (const int e = ensure_dynamic_smem(solver_rolled_kernel<T, BW, SYNC>, smem, false, configured))
@@ -289,9 +291,11 @@ template <int T, int BW>
 static int launch_rolled(const RolledGeom& g, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
-    if (g_stream_pair)
-        return launch_rolled_impl<T, BW, 1>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-    return launch_rolled_impl<T, BW, 0>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    if constexpr (T % 2 == 0) {   // the CTA-barrier form (a test hook) is built for the even depths only
+        if (!g_stream_pair)
+            return launch_rolled_impl<T, BW, 0>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    }
+    return launch_rolled_impl<T, BW, 1>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
 }
 
 // band widths per depth: what the register file allows (T = 10: 40 + 20 + 48 state registers -> 168 per thread ->
@@ -303,7 +307,7 @@ static int launch_rolled_best(const float* coefA, const float* coefB, const floa
     const int L = 3 * W, sms = sm_count();
     constexpr int NCAND = 4;
     const int cands[NCAND] = {512, 448, 384, 256};
-    constexpr int first = T >= 10 ? 2 : 0;   // T = 10: 384 and 256 only
+    constexpr int first = T >= 9 ? 2 : 0;   // T = 9, 10: 384 and 256 only
     int best = first;
     RolledGeom bg = rolled_geom(T, cands[first], L, H, sms);
     if (g_stream_band >= 1 && g_stream_band <= NCAND) {
@@ -318,7 +322,7 @@ static int launch_rolled_best(const float* coefA, const float* coefB, const floa
             }
         }
     }
-    if constexpr (T < 10) {
+    if constexpr (T < 9) {
         if (best == 0)
             return launch_rolled<T, 512>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
         if (best == 1)
@@ -327,6 +331,13 @@ static int launch_rolled_best(const float* coefA, const float* coefB, const floa
     if (best == 2)
         return launch_rolled<T, 384>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     return launch_rolled<T, 256>(bg, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+}
+
+// can this kernel take the passes of a solve at all (so that the planner may use odd depths)?
+bool solver_rolled_takes(int W, const void* a, const void* b, const void* c, const void* d)
+{
+    return g_stream_rolled && g_stream_coop && g_stream_pair && (3LL * W) % 4 == 0 && aligned16(a) && aligned16(b)
+        && aligned16(c) && aligned16(d);
 }
 
 // true if this kernel can run the pass (then *rc is its status); false: the caller uses stab_solver_stream.cu
@@ -350,6 +361,10 @@ bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const flo
         case 6: *rc = launch_rolled_best<6>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
         case 4: *rc = launch_rolled_best<4>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
         case 2: *rc = launch_rolled_best<2>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
+        case 9: *rc = launch_rolled_best<9>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
+        case 7: *rc = launch_rolled_best<7>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
+        case 5: *rc = launch_rolled_best<5>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
+        case 3: *rc = launch_rolled_best<3>(coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st); return true;
         default: return false;
     }
 }
