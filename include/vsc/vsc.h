@@ -89,9 +89,10 @@ VSC_API uint64_t vsc_launch_count(void);
 VSC_API int vsc_correlation_f32(const float* in1, const float* in2, float* out, int N, int C, int H, int W,
     int max_displacement, int legacy, vsc_stream_t stream);
 
-/* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases; 64x8 tiles
- * for W >= 96, else 32x8), plain loads otherwise;  1: always the plain-load stager;  2 / 3: TMA with 32x8 / 64x8
- * tiles -- same arithmetic, bit-identical results;  4: the channel-split kernel that mode 0 uses for maps of at
+/* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases; skewed 64x8
+ * tiles whose lane pairs share their in2 rows for W >= 96, else 32x8), plain loads otherwise;  1: always the
+ * plain-load stager;  2 / 3 / 5 / 6: TMA with 32x8 / 64x8 / skewed shared-row 64x8 / skewed shared-row 32x8 tiles
+ * -- same arithmetic, bit-identical results;  4: the channel-split kernel that mode 0 uses for maps of at
  * most 12288 pixels (8 partial sums per value: equal within rounding).  For tests. */
 VSC_API int vsc_set_correlation_mode(int mode);
 

@@ -18,6 +18,7 @@ import torch  # noqa: E402
 import vsc_b200 as V  # noqa: E402
 
 label = sys.argv[1] if len(sys.argv) > 1 else "default"
+V.check(V.lib().vsc_set_correlation_mode(int(os.environ.get("VSC_CORR_MODE", "0"))))
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
 g = torch.Generator(device=dev).manual_seed(0)

@@ -1,6 +1,6 @@
 // Micro-benchmark: how many shared-memory wavefronts does one LDS.128 cost when several lanes of a warp read the SAME
 // 16 bytes?  (Design question for custom::Correlation: lanes of different displacement groups that share in2 rows.)
-// Patterns (quad index read by lane l):  0: l (512 B unique)   1: l % 16 (two half-warps read the same 256 B)
+// Patterns 6-10: the lane layouts of correlation_md4_share_kernel.  Patterns (quad index read by lane l):  0: l (512 B unique)   1: l % 16 (two half-warps read the same 256 B)
 //   2: l / 2 (adjacent lane pairs share)   3: l % 8 (128 B unique)   4: 0 (one quad)
 //   5: (l % 8) + 18 * (l / 24)  (three groups of 8 lanes share one 128 B row segment, the fourth reads another row)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o lds_merge lds_merge.cu ; run: ./lds_merge
@@ -21,7 +21,12 @@ __global__ void __launch_bounds__(384, 1) k(int pattern, int iters, float* out, 
         case 2: q = l / 2; break;
         case 3: q = l % 8; break;
         case 4: q = 0; break;
-        default: q = (l % 8) + 18 * (l / 24); break;
+        case 5: q = (l % 8) + 18 * (l / 24); break;
+        case 6: q = l / 3; break;                          // items (quad, member) flattened: 3 lanes per quad
+        case 7: q = (l + 16) / 3; break;                   // the same, other phase
+        case 8: q = l / 3 + 17 * 3 * (l % 3); break;       // in1: member m reads row 3m of a 68-float-stride tile
+        case 9: q = (l + 16) / 3 + 17 * 3 * ((l + 16) % 3); break;
+        default: q = l / 3 + 16 * 3 * (l % 3); break;      // in1 with 64-float rows: bank conflicts expected
     }
     q += (threadIdx.x >> 5) * 32;   // every warp its own region
     float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
@@ -54,10 +59,10 @@ int main()
     cudaMalloc(&out, 148 * 384 * sizeof(float));
     cudaMallocManaged(&cyc, sizeof(long long));
     const int iters = 20000;
-    const char* names[6] = {"32 distinct quads (512 B)", "l%16: half-warps share (256 B)", "l/2: lane pairs share (256 B)",
-        "l%8 (128 B)", "one quad (16 B)", "3 groups share + 1 other row (256 B)"};
+    const char* names[11] = {"32 distinct quads (512 B)", "l%16: half-warps share (256 B)", "l/2: lane pairs share (256 B)",
+        "l%8 (128 B)", "one quad (16 B)", "3 groups share + 1 other row (256 B)", "l/3: three lanes per quad", "(l+16)/3", "in1 rows 3 apart, stride 68", "same, other phase", "in1 rows 3 apart, stride 64"};
     for (int warps = 4; warps <= 12; warps += 8)
-        for (int pat = 0; pat < 6; ++pat) {
+        for (int pat = 0; pat < 11; ++pat) {
             k<<<148, warps * 32>>>(pat, 100, out, cyc);
             cudaDeviceSynchronize();
             k<<<148, warps * 32>>>(pat, iters, out, cyc);

@@ -243,6 +243,10 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
         tma32 = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(3) == 0   # TMA, 64x8 tiles, software-pipelined, 1 CTA per SM
         tma64 = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(5) == 0   # TMA, skewed 64x8 tiles, lane pairs share their in2 rows
+        share = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(6) == 0   # the same with 32x8 tiles, two CTAs of 6 warps per SM
+        share32 = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(4) == 0   # channel-split kernel (small maps)
         split = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(0) == 0
@@ -253,6 +257,8 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
     torch.cuda.synchronize()
     assert torch.equal(tma32, plain)
     assert torch.equal(tma64, plain)
+    assert torch.equal(share, plain)
+    assert torch.equal(share32, plain)
     tol = 5e-6 * max(float(plain.abs().max()), 1e-30)   # 8 partial sums per value: equal within rounding
     assert float((split - plain).abs().max()) <= tol
     if H * W <= 12288:   # auto = channel-split kernel

@@ -112,29 +112,52 @@ __device__ __forceinline__ void correlate_chunk(const float* __restrict__ sA, co
     }
 }
 
-__device__ __forceinline__ void correlation_store(float* __restrict__ out, const float (&acc)[3][kP][4], int n, int g,
-    int y, int x, int H, int W, float divisor, int legacy, int vec_store)
+// The 108 values of a thread leave as 27 streaming 128-bit stores.  The epilogue is kept LEAN on purpose: ncu's
+// per-instruction samples of the 64x8 kernel (profiles/r2_correlation_ncu.txt) put a third of all warp time into the
+// old epilogue -- 38 instructions per store (a 64-bit address product, the legacy select and the alignment test
+// inside the loops) run once per tile from a cold instruction cache while the FMA pipes idle.  Here: one base
+// pointer, one 64-bit add per store, the legacy division and the unaligned case hoisted out of the loops.
+// rot: slot i of the thread holds vertical displacement 3g + (i + rot) % 3 (the shared-row kernel's odd lanes).
+__device__ __forceinline__ void correlation_store(float* __restrict__ out, float (&acc)[3][kP][4], int n, int g, int y,
+    int x, int H, int W, float divisor, int legacy, int vec_store, int rot = 0)
 {
-    if (y >= H || x >= W)
+    if (y < 0 || y >= H || x >= W)
         return;
     const size_t HW = static_cast<size_t>(H) * W;
+    if (legacy) {  // total_sum / (float)C, a true division (correlation_cuda.cu:259-261)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int ph = 3 * g + i;
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < kP; ++j) {
-            float* o = out + ((static_cast<size_t>(n) * kP + ph) * kP + j) * HW + static_cast<size_t>(y) * W + x;
-            float v[4];
+            for (int j = 0; j < kP; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // legacy: total_sum / (float)C, a true division (correlation_cuda.cu:259-261)
-                v[k] = legacy ? acc[i][j][k] / divisor : acc[i][j][k];
-            if (vec_store) {  // W % 4 == 0 and out 16B-aligned: x+3 < W holds as well
-                stg_stream4(o, make_float4(v[0], v[1], v[2], v[3]));
-            } else {
+                for (int k = 0; k < 4; ++k)
+                    acc[i][j][k] = acc[i][j][k] / divisor;
+    }
+    float* base = out + (static_cast<size_t>(n) * kP + 3 * g) * kP * HW + static_cast<size_t>(y) * W + x;
+    const size_t plane = kP * HW;
+    if (vec_store) {  // W % 4 == 0 and out 16B-aligned: x+3 < W holds as well
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int sh = (i + rot >= 3) ? i + rot - 3 : i + rot;
+            float* o = base + sh * plane;
+#pragma unroll
+            for (int j = 0; j < kP; ++j) {
+                stg_stream4(o, make_float4(acc[i][j][0], acc[i][j][1], acc[i][j][2], acc[i][j][3]));
+                o += HW;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int sh = (i + rot >= 3) ? i + rot - 3 : i + rot;
+            float* o = base + sh * plane;
+#pragma unroll
+            for (int j = 0; j < kP; ++j) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (x + k < W)
-                        o[k] = v[k];
+                        o[k] = acc[i][j][k];
+                o += HW;
             }
         }
     }
@@ -354,6 +377,304 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
     }
 }
 
+// ---- shared-row kernel: the 64x8 persistent kernel with lane PAIRS that read the same in2 addresses ---------
+// The kernel above is bound by the shared-memory crossbar: per channel a warp issues 10 LDS.128 = 40 wavefronts for
+// 108 FFMAs = 27 SM-cycles of the FMA pipes.  Measured on the B200 (profiles/ubench/lds_merge.cu): an LDS.128 whose
+// lanes 2i and 2i+1 read the SAME 16 bytes costs 2.16 cycles instead of 4.00 -- the two quarter-warps of a half-warp
+// are served by one 128-byte wavefront.  (Sharing between other lane groupings -- half-warps, lanes l/3, l%8 -- is
+// NOT merged: 4.00.)  So the lanes of a warp are laid out as 16 pixel quads x 2 MEMBERS that need the same in2
+// rows at every load:
+//   * a thread still owns 4 px x 9 x 3 displacements.  With pixel row p and vertical displacements dy = 3g-4+i it
+//     reads in2 rows p + 3g - 4 + i.  The tile is SKEWED: for the staged in2 rows R0 .. R0+9 and k = 0..7, member
+//     (g, k) owns pixel row p = R0 + k + 4 - 3g, so that all three groups g of one k read in2 rows R0+k .. R0+k+2
+//     (in1 rows R0-2 .. R0+11 are staged: 14 x 80 + 10 x 72 floats per channel instead of 8 x 64 + 16 x 72);
+//   * warps 0..7: lanes (2q, 2q+1) = groups g = 0, 1 of k = warp: every in2 load is pair-shared (2 wavefronts);
+//   * warps 8..11: lanes (2q, 2q+1) = group g = 2 of k and of k+1; the odd lane walks its three rows rotated
+//     (k+3, k+1, k+2), so two of its three rows coincide with the even lane's (k, k+1, k+2): 6 of 9 loads shared;
+//   * in1 rows are 80 floats apart (64 + 8 columns either side): the two members' rows are 3 (or 1) rows apart =
+//     16 banks mod 32, so the in1 load of a quarter-warp (4 quads of each row) is conflict-free.
+// Per warp and channel: 4 + 18 (warps 0-7) or 4 + 24 (warps 8-11) wavefronts against 40 before.  Every output is the
+// same sequential-over-c fp32 FMA chain as in the other kernels (bit-identical).
+constexpr int kSAW = kWTW + 16;                        // 80: in1 tile row
+constexpr int kSAH = kTH + 6;                          // 14 in1 rows
+constexpr int kSBH = kTH + 2;                          // 10 in2 rows
+constexpr int kSASize = kSAH * kSAW;                   // 1120
+constexpr int kSBSize = kSBH * kWBW;                   // 720
+constexpr int kSStageFloats = kKC * (kSASize + kSBSize);  // 14720 floats = 57.5 KB
+constexpr unsigned kSStageBytes = kSStageFloats * sizeof(float);
+#ifndef VSC_CORR_UNROLL
+#define VSC_CORR_UNROLL 1
+#endif
+#ifndef VSC_CORR_DEPTH
+#define VSC_CORR_DEPTH 1
+#endif
+constexpr int kSU = VSC_CORR_UNROLL;                   // channels per trip of the channel loop
+constexpr int kSD = VSC_CORR_DEPTH;                    // in2 loads in flight per thread
+static_assert(kKC % kSU == 0 && (9 * kSU) % kSD == 0 && kSD <= 9, "pipeline geometry");
+#ifndef VSC_CORR_FFMA2
+#define VSC_CORR_FFMA2 0
+#endif
+#ifndef VSC_CORR_NARROW_DEFAULT
+#define VSC_CORR_NARROW_DEFAULT 1
+#endif
+
+// packed pair of floats in a 64-bit register pair (sm_100a fma.rn.f32x2 -> FFMA2: two IEEE FMAs, one issue slot)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float(static_cast<unsigned>(v)); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float(static_cast<unsigned>(v >> 32)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// TW = 64: one CTA of 12 warps per SM.  TW = 32: CTAs of 6 warps, TWO per SM (168 registers x 192 threads x 2 fits
+// the register file): while one CTA stores its 108 accumulators per thread or waits at a chunk barrier, the other
+// keeps the FMA pipes busy (ncu on the 64-wide kernel: 17 % of all warp time in the per-tile code, 16 % in the
+// per-chunk code, all 12 warps in the same phase).
+template <int TW>
+__global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_share_kernel(
+    const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ out, int C,
+    int H, int W, float divisor, int legacy, int vec_store, int tiles_x, int tiles_y, int ntiles)
+{
+    constexpr int kThreads = TW * 6;                      // (TW / 4) quads x 8 rows x 3 groups
+    constexpr int kAW = TW + 16, kBWid = TW + 2 * kMD;    // staged row lengths: in1 80 / 48, in2 72 / 40 floats
+    constexpr int kASz = kSAH * kAW, kBSz = kSBH * kBWid;
+    constexpr int kStageF = kKC * (kASz + kBSz);
+    constexpr unsigned kStageB = kStageF * sizeof(float);
+    pdl_enter();
+    extern __shared__ __align__(128) unsigned char smem_bytes[];
+    float* stage_mem = reinterpret_cast<float*>(smem_bytes);
+    __shared__ __align__(8) unsigned long long bars[2 * kStages];  // full[0..2], empty[0..2]
+
+    const int tid = threadIdx.x;
+    const int nchunks = (C + kKC - 1) / kKC;
+    const unsigned bar0 = smem_u32(bars);
+    const int my_tiles = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int total = my_tiles * nchunks;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar0 + 8 * i, 1);
+            mbar_init(bar0 + 8 * (kStages + i), kThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tile -> first column, first staged in2 row R0 = 8 ty - 4, image
+    auto tile_coords = [&](int it, int& w0, int& R0, int& n) {
+        const int t = blockIdx.x + it * gridDim.x;
+        const int bx = t % tiles_x;
+        const int rest = t / tiles_x;
+        w0 = bx * TW;
+        R0 = (rest % tiles_y) * kTH - kMD;
+        n = rest / tiles_y;
+    };
+    auto issue = [&](int G) {
+        int w0, R0, n;
+        tile_coords(G / nchunks, w0, R0, n);
+        const int j = G % nchunks;
+        const int s = G % kStages;
+        const unsigned full = bar0 + 8 * s;
+        mbar_expect_tx(full, kStageB);
+        const unsigned dstA = smem_u32(stage_mem + s * kStageF);
+        const unsigned dstB = dstA + kKC * kASz * sizeof(float);
+        tma_load_4d(dstA, &mapA, full, w0 - 8, R0 - 2, j * kKC, n);
+        tma_load_4d(dstB, &mapB, full, w0 - kMD, R0, j * kKC, n);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (total > 1)
+            issue(1);
+    }
+
+    // a tile has 12 member PAIRS (lanes 2q, 2q+1 over its TW / 4 quads): pairs 0..7 = groups 0, 1 of k = pair, pairs
+    // 8..11 = group 2 of k = 2 (pair - 8) and k + 1.  A warp holds one pair (TW = 64) or two (TW = 32).
+    constexpr int kQuads = TW / 4;
+    const int pidx = tid >> 1;              // pair slot in the CTA
+    const int pair = pidx / kQuads;         // 0..11
+    const int qc = (pidx % kQuads) * 4;     // first tile column of the quad
+    const int mem = tid & 1;
+    // member -> group g, row index k, in2 row of slot 0 and of slot 1 (slot 2 = slot 1 + 1), rotation of the slots
+    int g, k, brow0, brow1, rot;
+    if (pair < 8) {
+        g = mem;
+        k = pair;
+        brow0 = k;
+        brow1 = k + 1;
+        rot = 0;
+    } else {
+        g = 2;
+        k = 2 * (pair - 8) + mem;
+        brow0 = mem ? k + 2 : k;
+        brow1 = mem ? k : k + 1;
+        rot = mem ? 2 : 0;   // slot s holds vertical displacement 3g + (s + rot) % 3
+    }
+    const int prow = k + 6 - 3 * g;           // in1 tile row of the member's pixel row
+    const int offA = prow * kAW + 8 + qc;
+    const int offB0 = kKC * kASz + brow0 * kBWid + qc;
+    const int offB1 = kKC * kASz + brow1 * kBWid + qc;
+#if VSC_CORR_FFMA2
+    // The loop is bound by instruction issue (ncu: the schedulers issue 97 % of the cycles spent in it; 108 FFMA + 10
+    // LDS + 19 others per channel).  The FMAs are therefore issued as packed pairs: the accumulators of pixel kk are
+    // paired over ADJACENT horizontal displacements so that both halves use in2 values b[m], b[m+1] with m EVEN, i.e.
+    // an aligned register pair of the 128-bit load: even kk pair (jj, jj+1) = (0,1) (2,3) (4,5) (6,7) and keep jj = 8
+    // single; odd kk pair (1,2) (3,4) (5,6) (7,8) and keep jj = 0 single.  The in1 value is duplicated into both
+    // halves once per channel.  Per row 4 x (4 FFMA2 + 1 FFMA) = 20 issue slots instead of 36; every lane of a packed
+    // FMA is the same IEEE operation, so results stay bit-identical.
+    f32x2 accp[3][4][4];
+    float accs[3][4];
+#else
+    float acc[3][kP][4];
+#endif
+
+    int G = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+#if VSC_CORR_FFMA2
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp)
+                    accp[i][kk][pp] = 0ull;
+                accs[i][kk] = 0.0f;
+            }
+#else
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < kP; ++j)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    acc[i][j][kk] = 0.0f;
+#endif
+
+        for (int j = 0; j < nchunks; ++j, ++G) {
+            const int s = G % kStages;
+            if (tid == 0 && G + 2 < total) {
+                if (G >= 1)
+                    mbar_wait(bar0 + 8 * (kStages + (G + 2) % kStages), ((G + 2) / kStages - 1) & 1);
+                issue(G + 2);
+            }
+            mbar_wait(bar0 + 8 * s, (G / kStages) & 1);
+            const float* st = stage_mem + s * kStageF;
+            const float* sA = st + offA;
+            const float* sB0 = st + offB0;
+            const float* sB1 = st + offB1;
+            // software pipeline: the in2 loads run kSD loads ahead of the FMAs they feed (a ring of kSD float4), the
+            // channel loop is unrolled kSU times so that the ring slots are compile-time registers
+            auto rowptr = [&](int i) { return i == 0 ? sB0 : sB1 + (i - 1) * kBWid; };
+#if VSC_CORR_FFMA2
+            ulonglong2 bq[kSD];
+#pragma unroll
+            for (int t = 0; t < kSD; ++t)
+                bq[t] = *reinterpret_cast<const ulonglong2*>(rowptr(t / 3) + 4 * (t % 3));
+            float4 an = *reinterpret_cast<const float4*>(sA);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kKC; c0 += kSU) {
+#pragma unroll
+                for (int u = 0; u < kSU; ++u) {
+                    const float av[4] = {an.x, an.y, an.z, an.w};
+                    const f32x2 a2[4] = {pk2(an.x, an.x), pk2(an.y, an.y), pk2(an.z, an.z), pk2(an.w, an.w)};
+                    if (u + 1 < kSU || c0 + kSU < kKC)
+                        an = *reinterpret_cast<const float4*>(sA + (c0 + u + 1) * kASz);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int i = t / 3, h = t % 3;
+                        const int slot = (u * 9 + t) % kSD;
+                        const f32x2 bp[2] = {bq[slot].x, bq[slot].y};
+                        const int un = u + (t + kSD) / 9, tn = (t + kSD) % 9;
+                        if (un < kSU || c0 + kSU < kKC)
+                            bq[slot] = *reinterpret_cast<const ulonglong2*>(rowptr(tn / 3) + (c0 + un) * kBSz + 4 * (tn % 3));
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int m = 4 * h + 2 * e;   // bp[e] = (b[m], b[m+1])
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const int jj = m - kk;     // displacement of the low half
+                                if (jj >= 0 && jj + 1 < kP) {
+                                    const int pp = (kk & 1) ? (jj - 1) / 2 : jj / 2;
+                                    accp[i][kk][pp] = fma2(a2[kk], bp[e], accp[i][kk][pp]);
+                                } else if (jj == kP - 1) {
+                                    accs[i][kk] = __fmaf_rn(av[kk], lo2(bp[e]), accs[i][kk]);
+                                } else if (jj == -1) {
+                                    accs[i][kk] = __fmaf_rn(av[kk], hi2(bp[e]), accs[i][kk]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#else
+            float4 bq[kSD];
+#pragma unroll
+            for (int t = 0; t < kSD; ++t)
+                bq[t] = *reinterpret_cast<const float4*>(rowptr(t / 3) + 4 * (t % 3));
+            float4 an = *reinterpret_cast<const float4*>(sA);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kKC; c0 += kSU) {
+#pragma unroll
+                for (int u = 0; u < kSU; ++u) {
+                    const float av[4] = {an.x, an.y, an.z, an.w};
+                    if (u + 1 < kSU || c0 + kSU < kKC)
+                        an = *reinterpret_cast<const float4*>(sA + (c0 + u + 1) * kASz);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int i = t / 3, h = t % 3;
+                        const int slot = (u * 9 + t) % kSD;
+                        const float bv[4] = {bq[slot].x, bq[slot].y, bq[slot].z, bq[slot].w};
+                        // the load kSD steps ahead: channel c0 + un, row i' = tn / 3, quad tn % 3
+                        const int un = u + (t + kSD) / 9, tn = (t + kSD) % 9;
+                        if (un < kSU || c0 + kSU < kKC)
+                            bq[slot] = *reinterpret_cast<const float4*>(rowptr(tn / 3) + (c0 + un) * kBSz + 4 * (tn % 3));
+#pragma unroll
+                        for (int mm = 0; mm < 4; ++mm) {
+                            const int m = 4 * h + mm;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const int jj = m - kk;
+                                if (jj >= 0 && jj < kP)
+                                    acc[i][jj][kk] = __fmaf_rn(av[kk], bv[mm], acc[i][jj][kk]);
+                            }
+                        }
+                    }
+                }
+            }
+#endif
+            __syncwarp();
+            if ((tid & 31) == 0)
+                mbar_arrive(bar0 + 8 * (kStages + s));
+        }
+        int w0, R0, n;
+        tile_coords(it, w0, R0, n);
+#if VSC_CORR_FFMA2
+        float acc[3][kP][4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int jj = 0; jj < kP; ++jj) {
+                    const int single = (kk & 1) ? 0 : kP - 1;
+                    const int off = (kk & 1) ? jj - 1 : jj;   // position among the paired displacements
+                    acc[i][jj][kk] = jj == single ? accs[i][kk]
+                        : (off & 1) ? hi2(accp[i][kk][off / 2]) : lo2(accp[i][kk][off / 2]);
+                }
+#endif
+        correlation_store(out, acc, n, g, R0 - 2 + prow, w0 + qc, H, W, divisor, legacy, vec_store, rot);
+    }
+}
+
 // ---- plain-load stager for shapes TMA cannot address (W % 4 != 0 or unaligned bases) ----------------
 __global__ void __launch_bounds__(kConsumers) correlation_md4_ld_kernel(const float* __restrict__ in1,
     const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float divisor, int legacy,
@@ -552,13 +873,14 @@ static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int
         == CUDA_SUCCESS;
 }
 
-int g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles, 4 channel-split (tests)
+int g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles, 4 channel-split (tests),
+                      // 5 / 6 TMA shared-row tiles, 64x8 (one CTA per SM) / 32x8 (two)
 
 }  // namespace vsc
 
 extern "C" int vsc_set_correlation_mode(int mode)
 {
-    if (mode < 0 || mode > 4)
+    if (mode < 0 || mode > 6)
         return VSC_E_INVALID;
     vsc::g_corr_mode = mode;
     return VSC_OK;
@@ -589,7 +911,35 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
         const float divisor = static_cast<float>(C);
         const bool tma_ok = g_corr_mode != 1 && (W % 4 == 0) && aligned16(in1) && aligned16(in2);
         // wide tile when it is not mostly padding: image at least 1.5 tiles wide (mode 2 / 3 force 32 / 64)
-        const bool wide = g_corr_mode == 3 || (g_corr_mode == 0 && W >= 96);
+        const bool wide = g_corr_mode == 3 || g_corr_mode == 5 || g_corr_mode == 6 || (g_corr_mode == 0 && W >= 96);
+        // shared-row lane layout (lane pairs read the same in2 rows): the default wide kernel; mode 3 keeps the
+        // one-row-per-half-warp layout for A/B runs
+        if (tma_ok && wide && g_corr_mode != 3) {
+            const bool narrow = g_corr_mode == 6 || (g_corr_mode == 0 && VSC_CORR_NARROW_DEFAULT);
+            const int TW = narrow ? 32 : 64;
+            CUtensorMap mapA, mapB;
+            if (make_map(&mapA, in1, N, C, H, W, TW + 16, kSAH) && make_map(&mapB, in2, N, C, H, W, TW + 2 * kMD, kSBH)) {
+                const size_t smem = static_cast<size_t>(kStages) * kKC * (kSAH * (TW + 16) + kSBH * (TW + 2 * kMD)) * sizeof(float);
+                static unsigned long long configured64 = 0, configured32 = 0;
+                if (const int e = narrow ? ensure_dynamic_smem(correlation_md4_share_kernel<32>, smem, true, configured32)
+                                         : ensure_dynamic_smem(correlation_md4_share_kernel<64>, smem, false, configured64))
+                    return e;
+                const int tiles_x = static_cast<int>(cdiv(W, TW));
+                const int tiles_y = (H > 2 ? (H - 2 + kTH - 1) / kTH : 0) + 1;   // skewed tiles: one more row of tiles
+                const long long ntiles = static_cast<long long>(tiles_x) * tiles_y * N;
+                if (ntiles > 0x7fffffffLL)
+                    return VSC_E_INVALID;
+                const long long slots = static_cast<long long>(sm_count()) * (narrow ? 2 : 1);
+                const unsigned ctas = static_cast<unsigned>(ntiles < slots ? ntiles : slots);
+                const int rc = narrow
+                    ? launch_pdl(correlation_md4_share_kernel<32>, dim3(ctas), dim3(192), smem, st, mapA, mapB, out, C, H, W,
+                          divisor, legacy ? 1 : 0, vec, tiles_x, tiles_y, static_cast<int>(ntiles))
+                    : launch_pdl(correlation_md4_share_kernel<64>, dim3(ctas), dim3(384), smem, st, mapA, mapB, out, C, H, W,
+                          divisor, legacy ? 1 : 0, vec, tiles_x, tiles_y, static_cast<int>(ntiles));
+                count_launch();
+                return rc ? rc : launch_status();
+            }
+        }
         if (tma_ok && wide) {
             CUtensorMap mapA, mapB;
             if (make_map(&mapA, in1, N, C, H, W, kWTW, kTH) && make_map(&mapB, in2, N, C, H, W, kWBW, kBH)) {
