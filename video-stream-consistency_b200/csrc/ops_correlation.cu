@@ -20,6 +20,8 @@
 //     reference's CPU kernel forms;
 //   * results leave as 128-bit streaming stores straight into the [N,9,9,H,W] layout (the legacy
 //     [N,81,H,W] layout is byte-identical; it only adds the division by C).
+// The default kernel for maps at least 96 pixels wide is correlation_md4_share_kernel<32> further down (skewed tiles
+// whose lane pairs read the same in2 rows, two CTAs of six warps per SM); this first kernel serves narrower maps.
 // TMA needs 16-byte aligned row strides (W % 4 == 0) and base pointers; other shapes take the same
 // compute loop behind a plain-load stager.  Any max_displacement other than 4 takes a one-thread-
 // per-output kernel (no shipped model uses one; model_spec.py:161-162).
@@ -395,13 +397,16 @@ __global__ void __launch_bounds__(kWThreads, 1) correlation_md4_tma64_kernel(
 //     16 banks mod 32, so the in1 load of a quarter-warp (4 quads of each row) is conflict-free.
 // Per warp and channel: 4 + 18 (warps 0-7) or 4 + 24 (warps 8-11) wavefronts against 40 before.  Every output is the
 // same sequential-over-c fp32 FMA chain as in the other kernels (bit-identical).
-constexpr int kSAW = kWTW + 16;                        // 80: in1 tile row
 constexpr int kSAH = kTH + 6;                          // 14 in1 rows
 constexpr int kSBH = kTH + 2;                          // 10 in2 rows
-constexpr int kSASize = kSAH * kSAW;                   // 1120
-constexpr int kSBSize = kSBH * kWBW;                   // 720
-constexpr int kSStageFloats = kKC * (kSASize + kSBSize);  // 14720 floats = 57.5 KB
-constexpr unsigned kSStageBytes = kSStageFloats * sizeof(float);
+#ifndef VSC_CORR_SKC
+#define VSC_CORR_SKC 8
+#endif
+#ifndef VSC_CORR_SSTAGES
+#define VSC_CORR_SSTAGES 3
+#endif
+constexpr int kSKC = VSC_CORR_SKC;                     // channels per stage of the shared-row kernel
+constexpr int kSStages = VSC_CORR_SSTAGES;             // ring depth
 #ifndef VSC_CORR_UNROLL
 #define VSC_CORR_UNROLL 1
 #endif
@@ -410,7 +415,7 @@ constexpr unsigned kSStageBytes = kSStageFloats * sizeof(float);
 #endif
 constexpr int kSU = VSC_CORR_UNROLL;                   // channels per trip of the channel loop
 constexpr int kSD = VSC_CORR_DEPTH;                    // in2 loads in flight per thread
-static_assert(kKC % kSU == 0 && (9 * kSU) % kSD == 0 && kSD <= 9, "pipeline geometry");
+static_assert(kSKC % kSU == 0 && (9 * kSU) % kSD == 0 && kSD <= 9, "pipeline geometry");
 #ifndef VSC_CORR_FFMA2
 #define VSC_CORR_FFMA2 0
 #endif
@@ -447,24 +452,24 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
     constexpr int kThreads = TW * 6;                      // (TW / 4) quads x 8 rows x 3 groups
     constexpr int kAW = TW + 16, kBWid = TW + 2 * kMD;    // staged row lengths: in1 80 / 48, in2 72 / 40 floats
     constexpr int kASz = kSAH * kAW, kBSz = kSBH * kBWid;
-    constexpr int kStageF = kKC * (kASz + kBSz);
+    constexpr int kStageF = kSKC * (kASz + kBSz);
     constexpr unsigned kStageB = kStageF * sizeof(float);
     pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_bytes[];
     float* stage_mem = reinterpret_cast<float*>(smem_bytes);
-    __shared__ __align__(8) unsigned long long bars[2 * kStages];  // full[0..2], empty[0..2]
+    __shared__ __align__(8) unsigned long long bars[2 * kSStages];  // full[0..2], empty[0..2]
 
     const int tid = threadIdx.x;
-    const int nchunks = (C + kKC - 1) / kKC;
+    const int nchunks = (C + kSKC - 1) / kSKC;
     const unsigned bar0 = smem_u32(bars);
     const int my_tiles = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int total = my_tiles * nchunks;
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kSStages; ++i) {
             mbar_init(bar0 + 8 * i, 1);
-            mbar_init(bar0 + 8 * (kStages + i), kThreads / 32);
+            mbar_init(bar0 + 8 * (kSStages + i), kThreads / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -483,18 +488,17 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
         int w0, R0, n;
         tile_coords(G / nchunks, w0, R0, n);
         const int j = G % nchunks;
-        const int s = G % kStages;
+        const int s = G % kSStages;
         const unsigned full = bar0 + 8 * s;
         mbar_expect_tx(full, kStageB);
         const unsigned dstA = smem_u32(stage_mem + s * kStageF);
-        const unsigned dstB = dstA + kKC * kASz * sizeof(float);
-        tma_load_4d(dstA, &mapA, full, w0 - 8, R0 - 2, j * kKC, n);
-        tma_load_4d(dstB, &mapB, full, w0 - kMD, R0, j * kKC, n);
+        const unsigned dstB = dstA + kSKC * kASz * sizeof(float);
+        tma_load_4d(dstA, &mapA, full, w0 - 8, R0 - 2, j * kSKC, n);
+        tma_load_4d(dstB, &mapB, full, w0 - kMD, R0, j * kSKC, n);
     };
     if (tid == 0) {
-        issue(0);
-        if (total > 1)
-            issue(1);
+        for (int G0 = 0; G0 < kSStages - 1 && G0 < total; ++G0)
+            issue(G0);
     }
 
     // a tile has 12 member PAIRS (lanes 2q, 2q+1 over its TW / 4 quads): pairs 0..7 = groups 0, 1 of k = pair, pairs
@@ -521,8 +525,8 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
     }
     const int prow = k + 6 - 3 * g;           // in1 tile row of the member's pixel row
     const int offA = prow * kAW + 8 + qc;
-    const int offB0 = kKC * kASz + brow0 * kBWid + qc;
-    const int offB1 = kKC * kASz + brow1 * kBWid + qc;
+    const int offB0 = kSKC * kASz + brow0 * kBWid + qc;
+    const int offB1 = kSKC * kASz + brow1 * kBWid + qc;
 #if VSC_CORR_FFMA2
     // The loop is bound by instruction issue (ncu: the schedulers issue 97 % of the cycles spent in it; 108 FFMA + 10
     // LDS + 19 others per channel).  The FMAs are therefore issued as packed pairs: the accumulators of pixel kk are
@@ -560,13 +564,13 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
 #endif
 
         for (int j = 0; j < nchunks; ++j, ++G) {
-            const int s = G % kStages;
-            if (tid == 0 && G + 2 < total) {
+            const int s = G % kSStages;
+            if (tid == 0 && G + kSStages - 1 < total) {   // refill the stage consumed at chunk G-1
                 if (G >= 1)
-                    mbar_wait(bar0 + 8 * (kStages + (G + 2) % kStages), ((G + 2) / kStages - 1) & 1);
-                issue(G + 2);
+                    mbar_wait(bar0 + 8 * (kSStages + (G + kSStages - 1) % kSStages), ((G + kSStages - 1) / kSStages - 1) & 1);
+                issue(G + kSStages - 1);
             }
-            mbar_wait(bar0 + 8 * s, (G / kStages) & 1);
+            mbar_wait(bar0 + 8 * s, (G / kSStages) & 1);
             const float* st = stage_mem + s * kStageF;
             const float* sA = st + offA;
             const float* sB0 = st + offB0;
@@ -581,12 +585,12 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
                 bq[t] = *reinterpret_cast<const ulonglong2*>(rowptr(t / 3) + 4 * (t % 3));
             float4 an = *reinterpret_cast<const float4*>(sA);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kKC; c0 += kSU) {
+            for (int c0 = 0; c0 < kSKC; c0 += kSU) {
 #pragma unroll
                 for (int u = 0; u < kSU; ++u) {
                     const float av[4] = {an.x, an.y, an.z, an.w};
                     const f32x2 a2[4] = {pk2(an.x, an.x), pk2(an.y, an.y), pk2(an.z, an.z), pk2(an.w, an.w)};
-                    if (u + 1 < kSU || c0 + kSU < kKC)
+                    if (u + 1 < kSU || c0 + kSU < kSKC)
                         an = *reinterpret_cast<const float4*>(sA + (c0 + u + 1) * kASz);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
                         const int slot = (u * 9 + t) % kSD;
                         const f32x2 bp[2] = {bq[slot].x, bq[slot].y};
                         const int un = u + (t + kSD) / 9, tn = (t + kSD) % 9;
-                        if (un < kSU || c0 + kSU < kKC)
+                        if (un < kSU || c0 + kSU < kSKC)
                             bq[slot] = *reinterpret_cast<const ulonglong2*>(rowptr(tn / 3) + (c0 + un) * kBSz + 4 * (tn % 3));
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
@@ -622,11 +626,11 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
                 bq[t] = *reinterpret_cast<const float4*>(rowptr(t / 3) + 4 * (t % 3));
             float4 an = *reinterpret_cast<const float4*>(sA);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kKC; c0 += kSU) {
+            for (int c0 = 0; c0 < kSKC; c0 += kSU) {
 #pragma unroll
                 for (int u = 0; u < kSU; ++u) {
                     const float av[4] = {an.x, an.y, an.z, an.w};
-                    if (u + 1 < kSU || c0 + kSU < kKC)
+                    if (u + 1 < kSU || c0 + kSU < kSKC)
                         an = *reinterpret_cast<const float4*>(sA + (c0 + u + 1) * kASz);
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
                         const float bv[4] = {bq[slot].x, bq[slot].y, bq[slot].z, bq[slot].w};
                         // the load kSD steps ahead: channel c0 + un, row i' = tn / 3, quad tn % 3
                         const int un = u + (t + kSD) / 9, tn = (t + kSD) % 9;
-                        if (un < kSU || c0 + kSU < kKC)
+                        if (un < kSU || c0 + kSU < kSKC)
                             bq[slot] = *reinterpret_cast<const float4*>(rowptr(tn / 3) + (c0 + un) * kBSz + 4 * (tn % 3));
 #pragma unroll
                         for (int mm = 0; mm < 4; ++mm) {
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(TW * 6, TW == 64 ? 1 : 2) correlation_md4_shar
 #endif
             __syncwarp();
             if ((tid & 31) == 0)
-                mbar_arrive(bar0 + 8 * (kStages + s));
+                mbar_arrive(bar0 + 8 * (kSStages + s));
         }
         int w0, R0, n;
         tile_coords(it, w0, R0, n);
@@ -856,7 +860,7 @@ static EncodeTiledFn encode_tiled()
 }
 
 // [N][C][H][W] fp32, box [1][KC][bh][bw]; out-of-bounds elements read as zero
-static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int W, int bw, int bh)
+static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int W, int bw, int bh, int kc = kKC)
 {
     EncodeTiledFn enc = encode_tiled();
     if (!enc)
@@ -865,7 +869,7 @@ static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int
         static_cast<cuuint64_t>(N)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 4, static_cast<cuuint64_t>(W) * H * 4,
         static_cast<cuuint64_t>(W) * H * C * 4};
-    const cuuint32_t box[4] = {static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), kKC, 1};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(kc), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -918,8 +922,8 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
             const bool narrow = g_corr_mode == 6 || (g_corr_mode == 0 && VSC_CORR_NARROW_DEFAULT);
             const int TW = narrow ? 32 : 64;
             CUtensorMap mapA, mapB;
-            if (make_map(&mapA, in1, N, C, H, W, TW + 16, kSAH) && make_map(&mapB, in2, N, C, H, W, TW + 2 * kMD, kSBH)) {
-                const size_t smem = static_cast<size_t>(kStages) * kKC * (kSAH * (TW + 16) + kSBH * (TW + 2 * kMD)) * sizeof(float);
+            if (make_map(&mapA, in1, N, C, H, W, TW + 16, kSAH, kSKC) && make_map(&mapB, in2, N, C, H, W, TW + 2 * kMD, kSBH, kSKC)) {
+                const size_t smem = static_cast<size_t>(kSStages) * kSKC * (kSAH * (TW + 16) + kSBH * (TW + 2 * kMD)) * sizeof(float);
                 static unsigned long long configured64 = 0, configured32 = 0;
                 if (const int e = narrow ? ensure_dynamic_smem(correlation_md4_share_kernel<32>, smem, true, configured32)
                                          : ensure_dynamic_smem(correlation_md4_share_kernel<64>, smem, false, configured64))
