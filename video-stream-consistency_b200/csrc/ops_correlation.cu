@@ -877,7 +877,7 @@ static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int
         == CUDA_SUCCESS;
 }
 
-int g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles, 4 channel-split (tests),
+std::atomic<int> g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles, 4 channel-split (tests),
                       // 5 / 6 TMA shared-row tiles, 64x8 (one CTA per SM) / 32x8 (two)
 
 }  // namespace vsc

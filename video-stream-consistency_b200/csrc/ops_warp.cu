@@ -180,14 +180,14 @@ __global__ void __launch_bounds__(kWarpTileW * kWarpTileH) warp_nchw_quad_kernel
         __stcs(op, sample(pt, pb));
 }
 
-int g_warp_mode = 0;    // 0 default, 1 linear one-pixel-per-thread kernel, 2 tiled, 3 quad addressing, flattened,
+std::atomic<int> g_warp_mode = 0;    // 0 default, 1 linear one-pixel-per-thread kernel, 2 tiled, 3 quad addressing, flattened,
                         // 4 TMA-staged tiles wherever applicable (ops_warp_staged.cu)
 bool warp_staged_applicable(const float* in, int N, int C, int H, int W);
 int launch_warp_staged(const float* in, const float* flow, float* out, int N, int C, int H, int W, int nchunk_req,
     cudaStream_t st, bool* launched);
 // smallest map the staged kernel takes by default (measured: profiles/r2_warp_staged_events.txt)
 constexpr long long kWarpStagedMinPixels = 120000;
-int g_warp_nchunk = 0;  // 0 = automatic channel split of the linear kernel, else the number of channel chunks
+std::atomic<int> g_warp_nchunk = 0;  // 0 = automatic channel split of the linear kernel, else the number of channel chunks
 
 }  // namespace vsc
 
@@ -241,7 +241,7 @@ extern "C" int vsc_warp_nchw_f32(const float* in, const float* flow, float* out,
     int nchunk = static_cast<int>((want + static_cast<long long>(gx) * N - 1) / (static_cast<long long>(gx) * N));
     if (nchunk < 1) nchunk = 1;
     if (nchunk > (C + 7) / 8) nchunk = (C + 7) / 8;
-    if (g_warp_nchunk > 0) nchunk = g_warp_nchunk < C ? g_warp_nchunk : C;
+    if (const int forced = g_warp_nchunk; forced > 0) nchunk = forced < C ? forced : C;
     if (nchunk > 65535) nchunk = 65535;
     int chunk = (C + nchunk - 1) / nchunk;
     chunk = (chunk + 3) / 4 * 4;  // whole unrolled groups

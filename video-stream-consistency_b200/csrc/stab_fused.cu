@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256, 4) stage_a_rows_kernel(StageAPtrs P, int 
 // vsc_set_stage_a_mode: low 4 bits = kernel (0 default = 3 with 128-thread CTAs, 1 one row per CTA, 2 row walk,
 // 3 row walk + flow prefetch, 4 row walk + loads one row ahead); bits 4-7 = log2(rows per CTA), 0 = 8 (fewer on
 // small frames), or bits 12-19 = rows per CTA as a number; bit 8 = 128-thread CTAs
-int g_stage_a_mode = 0;
+std::atomic<int> g_stage_a_mode = 0;
 // rows per CTA forced by the mode word: bits 12-19 = the number itself, else bits 4-7 = its log2, else 0 (automatic)
 static int stage_a_rows_forced()
 {

@@ -175,14 +175,14 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 // implemented in stab_solver_rolled.cu: the same passes with a 4-step loop (16-byte aligned rows); false = not applicable
 bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st, int* rc);
-extern int g_stream_rolled;
+extern std::atomic<int> g_stream_rolled;
 
-int g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
-extern bool g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
-extern int g_stream_band, g_stream_edge_top, g_stream_edge_bot;
-bool g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
+std::atomic<int> g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
+extern std::atomic<bool> g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
+extern std::atomic<int> g_stream_band, g_stream_edge_top, g_stream_edge_bot;
+std::atomic<bool> g_frame_fused = true;                 // vsc_frame_stabilize: fused stage A + solver set-up when possible
 
-int g_stream_tmain = 0;                     // deepest blocked pass: 0 = chosen per solve, else 8 or 10
+std::atomic<int> g_stream_tmain = 0;                     // deepest blocked pass: 0 = chosen per solve, else 8 or 10
 
 // How `iters` sweeps are executed: n_hi blocked passes of t_hi sweeps, then n_lo passes of t_lo, then `rest` single
 // unblocked sweeps.  Every pass is exact Jacobi, so any partition gives the same result.
@@ -192,7 +192,7 @@ struct SweepPlan {
     int flips() const { return n_hi + n_lo + rest; }  // number of out-buffer ping-pongs
     int depth(int k) const { return k < n_hi ? t_hi : t_lo; }
 };
-bool g_plan_balanced = false;   // vsc_set_solver_mode(| 0x0800): passes of nearly equal depth, odd depths included
+std::atomic<bool> g_plan_balanced = false;   // vsc_set_solver_mode(| 0x0800): passes of nearly equal depth, odd depths included
 bool solver_rolled_takes(int W, const void* a, const void* b, const void* c, const void* d);   // stab_solver_rolled.cu
 
 // even_only: the passes will run in stab_solver_stream.cu (rows that are not 16-byte aligned, or by request), which
@@ -212,7 +212,8 @@ static SweepPlan plan_sweeps(int W, int H, int iters, bool even_only)
         // the default plan at 1080p (733 vs 741-746 frames/s sustained, profiles/r2_plan_balanced_ab.txt): passes of 9
         // and 10 sweeps need the 384-float bands (168 registers), and at 960x540 the wider bands of the 8-sweep passes
         // win back more than the two passes saved.  Kept as a tested option.
-        const int tmax = g_stream_tmain ? g_stream_tmain : (static_cast<long long>(W) * H >= 500000 ? 10 : 8);
+        const int forced_t = g_stream_tmain;
+        const int tmax = forced_t ? forced_t : (static_cast<long long>(W) * H >= 500000 ? 10 : 8);
         const int npass = (iters + tmax - 1) / tmax;
         const int base = iters / npass;
         p.n_hi = iters % npass;

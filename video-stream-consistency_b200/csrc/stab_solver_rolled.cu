@@ -39,12 +39,12 @@ namespace vsc {
 __host__ __device__ constexpr int rolled_halo(int T) { return (3 * T + 3) / 4 * 4; }
 // staging ring depth (rows in flight from HBM): about 2T, a multiple of 4 (the slot base advances by 4 per group)
 __host__ __device__ constexpr int rolled_pf(int T) { return (2 * T + 3) / 4 * 4 < 8 ? 8 : (2 * T + 3) / 4 * 4; }
-extern bool g_stream_pair;          // stab_solver_stream.cu: neighbour-pair named barriers (default) or CTA barrier
-extern bool g_stream_coop;          // false: per-thread 4-byte staging requested -> stab_solver_stream.cu
-extern int g_stream_band;           // 0 = cost model; 1..4 force a band width (512, 448, 384, 256)
-int g_stream_rolled = 1;            // 0: never use this kernel (vsc_set_solver_mode | 0x8000), 1: auto, 2: always (| 0x4000)
-int g_stream_edge_top = -1;         // rows by which the first / last row chunk is shorter than the others (-1: default)
-int g_stream_edge_bot = -1;
+extern std::atomic<bool> g_stream_pair;          // stab_solver_stream.cu: neighbour-pair named barriers (default) or CTA barrier
+extern std::atomic<bool> g_stream_coop;          // false: per-thread 4-byte staging requested -> stab_solver_stream.cu
+extern std::atomic<int> g_stream_band;           // 0 = cost model; 1..4 force a band width (512, 448, 384, 256)
+std::atomic<int> g_stream_rolled = 1;            // 0: never use this kernel (vsc_set_solver_mode | 0x8000), 1: auto, 2: always (| 0x4000)
+std::atomic<int> g_stream_edge_top = -1;         // rows by which the first / last row chunk is shorter than the others (-1: default)
+std::atomic<int> g_stream_edge_bot = -1;
 
 template <int T, int BW, int SYNC>
 __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __restrict__ coefA,
@@ -248,7 +248,8 @@ static RolledGeom rolled_geom(int T, int BW, int L, int H, int sms)
     if (nc > (H + min_rows - 1) / min_rows) nc = (H + min_rows - 1) / min_rows;
     if (nc < 1) nc = 1;
     // the first / last chunk run the masked copy for 3T / 2T steps: shorter by default (profiles/r2_solver_sweep_pairs_edges.txt)
-    int top = g_stream_edge_top >= 0 ? g_stream_edge_top : 8, bot = g_stream_edge_bot >= 0 ? g_stream_edge_bot : 4;
+    const int et = g_stream_edge_top, eb = g_stream_edge_bot;
+    int top = et >= 0 ? et : 8, bot = eb >= 0 ? eb : 4;
     if (nc < 3 || H < nc * (2 * T + top + bot)) top = bot = 0;
     // H = (mid - top) + (nc - 2) * mid + last,  last <= mid - bot
     g.chunk_rows = (H + top + bot + nc - 1) / nc;

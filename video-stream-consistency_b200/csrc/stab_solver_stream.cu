@@ -35,9 +35,9 @@ namespace vsc {
 // private staging depth: divides the unroll factor 2T (T in {2, 4, 6, 8})
 __host__ __device__ constexpr int stream_private_pf(int T) { return T == 6 ? 6 : (T == 2 ? 4 : (T == 10 ? 10 : 8)); }
 __host__ __device__ constexpr int stream_halo(int T) { return (3 * T + 3) / 4 * 4; }
-bool g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
-bool g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
-int g_stream_band = 0;              // 0 = cost model; 1..4 force a band candidate (benchmarks, vsc_set_solver_mode)
+std::atomic<bool> g_stream_coop = true;          // warp-cooperative 16-byte staging when the images allow it
+std::atomic<bool> g_stream_pair = true;          // neighbour-pair named barriers instead of a CTA-wide barrier
+std::atomic<int> g_stream_band = 0;              // 0 = cost model; 1..4 force a band candidate (benchmarks, vsc_set_solver_mode)
 
 // BW = band width in floats = threads per CTA (one CTA per SM; the launcher picks the BW that fills the SMs best.
 // Two 256-wide CTAs per SM were measured slower than every single-CTA geometry at every size from 640x360 to

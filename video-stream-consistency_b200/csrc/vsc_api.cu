@@ -5,7 +5,7 @@
 namespace vsc {
 
 unsigned long long g_launches = 0;
-bool g_pdl = true;
+std::atomic<bool> g_pdl = true;
 
 int sm_count()
 {

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "vsc/vsc.h"
 
 namespace vsc {
@@ -58,7 +60,7 @@ inline int ensure_dynamic_smem(Kernel kernel, size_t smem, bool max_carveout, un
 // wait returns once the predecessor grid has completed and flushed), and it calls pdl_trigger() first so that ITS
 // successor can be placed early as well.  Without the launch attribute both are no-ops, so the kernels can also be
 // launched the ordinary way.  The per-frame chain is ~45 dependent launches: this hides their launch latencies.
-extern bool g_pdl;   // vsc_set_solver_mode(| 0x80) turns it off (A/B runs)
+extern std::atomic<bool> g_pdl;   // vsc_set_solver_mode(| 0x80) turns it off (A/B runs)
 __device__ __forceinline__ void pdl_enter()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
