@@ -25,8 +25,8 @@ L = V.lib()
 for (N, C, H, W) in ((1, 12, 24, 128), (2, 9, 17, 40), (1, 20, 9, 15), (1, 5, 7, 33)):
     a = torch.randn((N, C, H, W), device=dev, generator=g)
     b = torch.randn((N, C, H, W), device=dev, generator=g)
-    for mode in (0, 1, 2, 3, 4):
-        if mode in (2, 3) and W % 4:
+    for mode in (0, 1, 2, 3, 4, 5, 6):   # 5 / 6: round-2 shared-row kernels (64- / 32-wide skewed tiles)
+        if mode in (2, 3, 5, 6) and W % 4:
             continue
         V.check(L.vsc_set_correlation_mode(mode))
         V.correlation(a, b)
@@ -53,7 +53,8 @@ for (W, H) in ((160, 96), (45, 37), (400, 64)):
     tg = torch.rand((H, W, 3), device=dev, generator=g)
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
     # (round 2: the default is the 4-step loop; 0x8000 = the fully unrolled form, 0x4000 forces the loop, edge fields)
-    for mode in (1, 2, 0x12, 0x22, 0x82, 0x1002, 0x2002, 0x2022, 0x8002, 0x8012, 0xA002, 0x6002, 2 | (17 << 16) | (11 << 22)):
+    for mode in (1, 2, 0x12, 0x22, 0x82, 0x1002, 0x2002, 0x2022, 0x8002, 0x8012, 0xA002, 0x6002, 2 | (17 << 16) | (11 << 22),
+                 0x0802, 0x2802):   # balanced plan: odd pass depths
         V.check(L.vsc_set_solver_mode(mode))
         for iters in (1, 9, 21):
             V.get_consist_out(pr, tg, wt, iters, 0.15, 0.15, pr.clone())
