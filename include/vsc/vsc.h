@@ -92,8 +92,9 @@ VSC_API int vsc_correlation_f32(const float* in1, const float* in2, float* out, 
 /* 0 (default): tiles staged by TMA when the tensors allow it (W % 4 == 0, 16-byte aligned bases; skewed 64x8
  * tiles whose lane pairs share their in2 rows for W >= 96, else 32x8), plain loads otherwise;  1: always the
  * plain-load stager;  2 / 3 / 5 / 6: TMA with 32x8 / 64x8 / skewed shared-row 64x8 / skewed shared-row 32x8 tiles
- * -- same arithmetic, bit-identical results;  4: the channel-split kernel that mode 0 uses for maps of at
- * most 12288 pixels (8 partial sums per value: equal within rounding).  For tests. */
+ * -- same arithmetic, bit-identical results;  4 / 7: the channel-split kernels that mode 0 uses for maps of at
+ * most 12288 pixels (one pixel / one 4-pixel quad per thread, the latter when W % 4 == 0; 4 - 16 partial sums per value:
+ * equal within rounding).  For tests. */
 VSC_API int vsc_set_correlation_mode(int mode);
 
 /* custom::Warp: masked bilinear backward warp (warp.cc:71-134 / warp_cuda.cu:29-84).

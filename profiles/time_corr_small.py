@@ -1,5 +1,5 @@
 """Event timing of custom::Correlation on the small (coarse PWC-Net) level shapes per kernel selection
-(vsc_set_correlation_mode: 4 = channel-split rows kernel, 6 = shared-row 32x8 tiles, 5 = 64x8, 0 = auto): back to back over two
+(vsc_set_correlation_mode: 4 = channel-split rows kernel, 7 = its quad form, 0 = auto; earlier runs: 6 / 5 = shared-row tiles): back to back over two
 tensor sets, and isolated with an L2 flush before every launch.  Not a bench.py number.
 
     python profiles/time_corr_small.py
@@ -21,12 +21,12 @@ torch.cuda.set_device(0)
 g = torch.Generator(device=dev).manual_seed(0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 L = V.lib()
-for (C, H, W) in ((64, 72, 120), (96, 36, 60), (128, 18, 30), (196, 9, 15), (128, 68, 120), (96, 136, 240), (64, 136, 240)):
+for (C, H, W) in ((64, 72, 120), (96, 36, 60), (128, 18, 30), (196, 9, 15), (128, 68, 120), (196, 34, 60), (64, 136, 88), (96, 136, 240), (64, 136, 240), (64, 272, 480), (32, 544, 960)):
     sets = [(torch.randn((1, C, H, W), device=dev, generator=g), torch.randn((1, C, H, W), device=dev, generator=g),
              torch.empty((1, 9, 9, H, W), device=dev)) for _ in range(2)]
     row = []
-    for mode in (0, 4, 6, 5):
-        if mode in (5, 6) and W % 4:
+    for mode in (0, 4, 7, 6):
+        if mode in (5, 6, 7) and W % 4:
             continue
         V.check(L.vsc_set_correlation_mode(mode))
         for s in sets:

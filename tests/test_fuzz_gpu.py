@@ -57,8 +57,8 @@ def test_fuzz_correlation_kernels_vs_oracle(V, O, dev):
             a, b = synth.features(N, C, H, W, 3), synth.features(N, C, H, W, 4)
             ref = O.correlation(a, b, legacy=legacy)
             scale = max(float(np.abs(ref).max()), 1e-30)
-            for mode in (0, 1, 2, 3, 4, 5, 6):
-                if mode in (2, 3, 5, 6) and W % 4:
+            for mode in (0, 1, 2, 3, 4, 5, 6, 7):
+                if mode in (2, 3, 5, 6, 7) and W % 4:
                     continue
                 assert L.vsc_set_correlation_mode(mode) == 0
                 got = V.correlation(cu(a, dev), cu(b, dev), legacy=legacy).cpu().numpy().reshape(ref.shape)

@@ -249,6 +249,8 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
         share32 = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(4) == 0   # channel-split kernel (small maps)
         split = V.correlation(a, b, legacy=legacy)
+        assert L.vsc_set_correlation_mode(7) == 0   # channel-split kernel with a 4-pixel register tile (W % 4 == 0)
+        quads = V.correlation(a, b, legacy=legacy)
         assert L.vsc_set_correlation_mode(0) == 0
         auto = V.correlation(a, b, legacy=legacy)
         auto2 = V.correlation(a, b, legacy=legacy)  # twice on the same stream (reference test.py:70-71)
@@ -261,8 +263,9 @@ def test_correlation_tma_and_plain_stagers_agree_bit_for_bit(V, dev, shape, lega
     assert torch.equal(share32, plain)
     tol = 5e-6 * max(float(plain.abs().max()), 1e-30)   # 8 partial sums per value: equal within rounding
     assert float((split - plain).abs().max()) <= tol
-    if H * W <= 12288:   # auto = channel-split kernel
-        assert torch.equal(auto, split)
+    assert float((quads - plain).abs().max()) <= tol
+    if H * W <= 12288:   # auto = channel-split kernel (its quad form when the rows are whole quads and aligned)
+        assert torch.equal(auto, quads if W % 4 == 0 else split)
     else:
         assert torch.equal(auto, plain)
     assert torch.equal(auto, auto2)

@@ -419,6 +419,9 @@ static_assert(kSKC % kSU == 0 && (9 * kSU) % kSD == 0 && kSD <= 9, "pipeline geo
 #ifndef VSC_CORR_FFMA2
 #define VSC_CORR_FFMA2 0
 #endif
+#ifndef VSC_CORR_ROWQUADS_DEFAULT
+#define VSC_CORR_ROWQUADS_DEFAULT 1
+#endif
 #ifndef VSC_CORR_NARROW_DEFAULT
 #define VSC_CORR_NARROW_DEFAULT 1
 #endif
@@ -837,6 +840,96 @@ __global__ void __launch_bounds__(32 * kSplitC) correlation_md4_rows_kernel(cons
     }
 }
 
+// The same channel-split scheme with a register tile for maps whose rows are whole 16-byte quads (W % 4 == 0, aligned
+// tensors): a thread owns one (ph, h, pixel QUAD) task = 4 px x 9 horizontal displacements = 36 accumulators and loads
+// per channel one 128-bit quad of in1 and the three quads of in2 around it -- 4 load instructions per 36 FMAs instead
+// of the 40 of the kernel above, which is bound by the number of load instructions it issues (1.1 per FMA).  Quads
+// lie entirely inside or outside a row, so the zero padding is two predicates.  Partial sums of the channel slices
+// are combined in slice order through shared memory; results leave as 128-bit stores.
+template <int kSplitC>
+__global__ void __launch_bounds__(32 * kSplitC) correlation_md4_rowquads_kernel(const float* __restrict__ in1,
+    const float* __restrict__ in2, float* __restrict__ out, int C, int H, int W, float scale, int use_div)
+{
+    pdl_enter();
+    __shared__ __align__(16) float part[kSplitC][kP][32][4];
+    __shared__ int obase[32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const unsigned HW = static_cast<unsigned>(H) * W;
+    const unsigned Wq = static_cast<unsigned>(W) / 4, HWq = static_cast<unsigned>(H) * Wq;
+    const unsigned tasks = kP * HWq;                      // per n: (ph, h, quad), quad fastest
+    const unsigned i = blockIdx.x * 32u + lane;
+    const int n = blockIdx.y;
+    float acc[kP][4];
+#pragma unroll
+    for (int j = 0; j < kP; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            acc[j][k] = 0.0f;
+    int ob = -1;
+    if (i < tasks) {
+        const unsigned ph = i / HWq;
+        const unsigned r = i - ph * HWq;
+        const int h = static_cast<int>(r / Wq);
+        const int w = 4 * static_cast<int>(r - static_cast<unsigned>(h) * Wq);
+        ob = static_cast<int>(ph * kP * HW + static_cast<unsigned>(h) * W + w);   // + pw * HW
+        const int h2 = h + static_cast<int>(ph) - kMD;
+        if (h2 >= 0 && h2 < H) {
+            const bool okL = w >= 4, okR = w + 4 < W;
+            const int cb = static_cast<int>(static_cast<long long>(C) * slice / kSplitC);
+            const int ce = static_cast<int>(static_cast<long long>(C) * (slice + 1) / kSplitC);
+            const float* a = in1 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h) * W + w;
+            const float* b = in2 + (static_cast<size_t>(n) * C + cb) * HW + static_cast<size_t>(h2) * W + w;
+            const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 2
+            for (int c = 0; c < ce - cb; ++c, a += HW, b += HW) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(a));
+                const float4 bl = okL ? __ldg(reinterpret_cast<const float4*>(b - 4)) : zero;
+                const float4 bm = __ldg(reinterpret_cast<const float4*>(b));
+                const float4 br = okR ? __ldg(reinterpret_cast<const float4*>(b + 4)) : zero;
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float bv[12] = {bl.x, bl.y, bl.z, bl.w, bm.x, bm.y, bm.z, bm.w, br.x, br.y, br.z, br.w};
+#pragma unroll
+                for (int m = 0; m < 12; ++m)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = m - k;
+                        if (j >= 0 && j < kP)
+                            acc[j][k] = __fmaf_rn(av[k], bv[m], acc[j][k]);
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kP; ++j)
+        *reinterpret_cast<float4*>(part[slice][j][lane]) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    if (slice == 0)
+        obase[lane] = ob;
+    __syncthreads();
+    // 9 x 32 quads per CTA: warp k sums displacement k (and k + kSplitC); 512-byte row stores
+    for (int j = slice; j < kP; j += kSplitC) {
+        const int o = obase[lane];
+        if (o >= 0) {
+            float4 sum = *reinterpret_cast<const float4*>(part[0][j][lane]);
+#pragma unroll
+            for (int k = 1; k < kSplitC; ++k) {
+                const float4 p = *reinterpret_cast<const float4*>(part[k][j][lane]);
+                sum.x += p.x;
+                sum.y += p.y;
+                sum.z += p.z;
+                sum.w += p.w;
+            }
+            if (use_div) {
+                sum.x = sum.x / scale;
+                sum.y = sum.y / scale;
+                sum.z = sum.z / scale;
+                sum.w = sum.w / scale;
+            }
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(n) * kP * kP * HW + static_cast<unsigned>(o)
+                + static_cast<size_t>(j) * HW) = sum;
+        }
+    }
+}
+
 // ---- host side: tensor maps ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -878,13 +971,13 @@ static bool make_map(CUtensorMap* m, const float* base, int N, int C, int H, int
 }
 
 std::atomic<int> g_corr_mode = 0;  // 0 auto, 1 plain-load stager, 2 TMA 32x8 tiles, 3 TMA 64x8 tiles, 4 channel-split (tests),
-                      // 5 / 6 TMA shared-row tiles, 64x8 (one CTA per SM) / 32x8 (two)
+                      // 5 / 6 TMA shared-row tiles, 64x8 (one CTA per SM) / 32x8 (two), 7 channel-split quads
 
 }  // namespace vsc
 
 extern "C" int vsc_set_correlation_mode(int mode)
 {
-    if (mode < 0 || mode > 6)
+    if (mode < 0 || mode > 7)
         return VSC_E_INVALID;
     vsc::g_corr_mode = mode;
     return VSC_OK;
@@ -906,7 +999,7 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
     // kernel, which spreads the work over 9*H*W/32 CTAs x 8 channel slices.  Its sums associate differently
     // from the tiled kernels' (8 partial sums), well inside the op's 1e-4 tolerance.
     const bool small_map = max_displacement == kMD
-        && (g_corr_mode == 4 || (g_corr_mode == 0 && static_cast<long long>(H) * W <= 12288));
+        && (g_corr_mode == 4 || g_corr_mode == 7 || (g_corr_mode == 0 && static_cast<long long>(H) * W <= 12288));
     if (max_displacement == kMD && !small_map) {
         const int vec = (W % 4 == 0) && aligned16(out);
         const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), N);
@@ -981,6 +1074,21 @@ extern "C" int vsc_correlation_f32(const float* in1, const float* in2, float* ou
     }
     const int P = 2 * max_displacement + 1;
     const size_t per_n = static_cast<size_t>(P) * P * H * W;
+    // quad form of the rows kernel: rows of whole 16-byte quads (mode 7 forces it, mode 4 forces the scalar form)
+    if (max_displacement == kMD && static_cast<long long>(H) * W * kP * kP < 0x7fffffffLL && W % 4 == 0 && aligned16(in1)
+        && aligned16(in2) && aligned16(out) && (g_corr_mode == 7 || (g_corr_mode == 0 && VSC_CORR_ROWQUADS_DEFAULT))) {
+        const dim3 grids(cdiv(static_cast<long long>(kP) * H * (W / 4), 32), N);
+        const float fC = static_cast<float>(C);
+        const int lg = legacy ? 1 : 0;
+        // about 16 channels per warp, at most 8 slices (36.9 KB of partial sums)
+        const int rc = C >= 96
+            ? launch_pdl(correlation_md4_rowquads_kernel<8>, grids, dim3(32 * 8), 0, st, in1, in2, out, C, H, W, fC, lg)
+            : launch_pdl(correlation_md4_rowquads_kernel<4>, grids, dim3(32 * 4), 0, st, in1, in2, out, C, H, W, fC, lg);
+        if (rc)
+            return rc;
+        count_launch();
+        return launch_status();
+    }
     if (max_displacement == kMD && static_cast<long long>(H) * W * kP * kP < 0x7fffffffLL) {
         const dim3 grids(cdiv(static_cast<long long>(kP) * H * W, 32), N);
         // channel slices per CTA: about 16 channels per warp (shorter slices drown in the per-task set-up and the
