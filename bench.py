@@ -470,8 +470,9 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
         torch.cuda.synchronize()
         return a.elapsed_time(b)
 
-    # the main pass of this image size: 10 sweeps per launch on large images, 8 below (stab_solver.cu, plan_sweeps)
-    T_main = 10 if W * H >= 900000 else 8
+    # the main pass: 8 sweeps per launch at every size since the quad-gather exchange ring (stab_solver.cu, plan_sweeps:
+    # 150 sweeps = 18 x 8 + 6)
+    T_main = 8
     force = args.solver_mode & ~0x3000 | (0x2000 if T_main == 10 else 0x1000)
     n = 16 * T_main
     L.vsc_set_solver_mode(force)

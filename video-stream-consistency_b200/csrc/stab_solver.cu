@@ -23,6 +23,10 @@
 // differs from it only in fp32 rounding (parity: tests/test_stab_gpu.py -- test_solver_vs_jacobi_oracle, test_sequence_vs_reference_gpu_fixtures; tolerances stated there).
 #include "vsc_common.cuh"
 
+#ifndef VSC_SOLVER_QG_DEFAULT
+#define VSC_SOLVER_QG_DEFAULT 1
+#endif
+
 namespace vsc {
 
 constexpr size_t kAlign = 256;
@@ -175,7 +179,7 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 // implemented in stab_solver_rolled.cu: the same passes with a 4-step loop (16-byte aligned rows); false = not applicable
 bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st, int* rc);
-extern std::atomic<int> g_stream_rolled;
+extern std::atomic<int> g_stream_rolled, g_stream_qg;
 
 std::atomic<int> g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern std::atomic<bool> g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
@@ -223,13 +227,15 @@ static SweepPlan plan_sweeps(int W, int H, int iters, bool even_only)
         p.rest = 0;
         return p;
     }
-    // main passes of 8 or 10 sweeps, one even tail pass, an odd sweep on its own.  10-sweep passes pay off on
-    // large images only (a pass costs 1.15-1.22x an 8-sweep pass from 720p up, more below), and only if they
-    // save enough passes: 150 = 15 x 10 against 18 x 8 + 6
+    // main passes of 8 or 10 sweeps, one even tail pass, an odd sweep on its own.  With the quad-gather exchange ring an
+    // 8-sweep pass costs 0.75 of a 10-sweep pass at every size (1080p 45.5 vs 60.9 us, 4K 143 vs 202 us, 960x540 18.2 vs
+    // 25.2 us: profiles/r2_solver_qg_sweep.txt), so 10-sweep passes are taken only where they save enough passes
+    // (150 = 18 x 8 + 6 beats 15 x 10; 20 = 2 x 10 beats 2 x 8 + 4)
     int tmain = 8;
     auto passes = [&](int t) { return iters / t + (((iters % t) & ~1) ? 1 : 0); };
     const bool large = static_cast<long long>(W) * H >= 900000;
-    if (g_stream_tmain == 10 || (g_stream_tmain == 0 && large && passes(10) * 121 < passes(8) * 100))
+    const int cost10 = g_stream_qg ? 134 : 121;   // cost of a 10-sweep pass in per cent of an 8-sweep pass
+    if (g_stream_tmain == 10 || (g_stream_tmain == 0 && large && passes(10) * cost10 < passes(8) * 100))
         tmain = 10;
     p.n_hi = iters / tmain;
     p.t_hi = tmain;
@@ -343,7 +349,7 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 extern "C" int vsc_set_solver_mode(int mode)
 {
     const int lo = mode & 0xFFFF;
-    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0xC000) == 0xC000 || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2 || (mode >> 28))
+    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0xC000) == 0xC000 || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2 || (mode >> 29))
         return VSC_E_INVALID;
     g_solver_mode = lo & 0xF;
     g_stream_pair = (lo & 0x10) == 0;
@@ -354,6 +360,7 @@ extern "C" int vsc_set_solver_mode(int mode)
     g_stream_band = (lo >> 8) & 7;
     g_stream_rolled = (lo & 0x8000) ? 0 : (lo & 0x4000) ? 2 : 1;
     g_plan_balanced = (lo & 0x0800) != 0;
+    g_stream_qg = ((mode >> 28) & 1) ? !VSC_SOLVER_QG_DEFAULT : VSC_SOLVER_QG_DEFAULT;
     g_stream_edge_top = ((mode >> 16) & 0x3F) - 1;   // 0 = default
     g_stream_edge_bot = ((mode >> 22) & 0x3F) - 1;
     return VSC_OK;

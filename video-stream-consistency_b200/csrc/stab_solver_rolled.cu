@@ -34,6 +34,10 @@
 
 #include "vsc_common.cuh"
 
+#ifndef VSC_SOLVER_QG_DEFAULT
+#define VSC_SOLVER_QG_DEFAULT 1
+#endif
+
 namespace vsc {
 
 __host__ __device__ constexpr int rolled_halo(int T) { return (3 * T + 3) / 4 * 4; }
@@ -45,8 +49,17 @@ extern std::atomic<int> g_stream_band;           // 0 = cost model; 1..4 force a
 std::atomic<int> g_stream_rolled = 1;            // 0: never use this kernel (vsc_set_solver_mode | 0x8000), 1: auto, 2: always (| 0x4000)
 std::atomic<int> g_stream_edge_top = -1;         // rows by which the first / last row chunk is shorter than the others (-1: default)
 std::atomic<int> g_stream_edge_bot = -1;
+std::atomic<int> g_stream_qg = VSC_SOLVER_QG_DEFAULT;   // 1: exchange ring in the quad-gather layout (vsc_set_solver_mode | 1 << 28 flips it)
 
-template <int T, int BW, int SYNC>
+// QG ("quad gather"): the exchange ring is laid out [slot][column][level] (LS floats per column) instead of
+// [level][slot][column], so that a thread fetches the left / right neighbours of FOUR time levels with one LDS.128 and
+// publishes its T new values with T/4 STS.128: 2 x ceil(T/4) + ceil(T/4) shared-memory instructions per step instead
+// of 3T.  All levels of a step read the same ring slot (written two steps earlier) and write the same slot, so the
+// batching changes no dependency.  LS = 12 floats (T > 4): 8 consecutive columns x 16 bytes then fall into 8 distinct
+// bank groups (12 i mod 32), i.e. every quarter-warp access is conflict-free.
+__host__ __device__ constexpr int rolled_ls(int T) { return T <= 4 ? 4 : 12; }
+
+template <int T, int BW, int SYNC, bool QG = false>
 __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, int first_rows, float step,
@@ -57,12 +70,15 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
     constexpr int PF = rolled_pf(T);   // staging ring depth (rows in flight from HBM); a multiple of 4
     constexpr int NX = 2 * T + 4;      // coefficient window: rows s0-2T .. s0+3 of a group starting at step s0
     static_assert(BW % 64 == 0 && PF % 4 == 0 && PF >= 8 && T >= 2, "geometry");
-    extern __shared__ float smem_raw[];
+    extern __shared__ __align__(16) float smem_raw[];
     // exchange ring: T*4 rows of RW = BW + 8 floats; the 8 floats between two rows are never written, so the band's
     // first / last three threads read 0.0f for their out-of-band neighbours
+    // (QG: 4 slots x RW columns x LS floats; column tid lives at physical column tid + 4, same zero margins)
     constexpr int RW = BW + 8;
+    constexpr int LS = rolled_ls(T);
+    constexpr int RING = QG ? 4 * RW * LS : T * 4 * RW + 8;   // floats
     float* sm = smem_raw + 4;
-    float* stage = smem_raw + T * 4 * RW + 8;   // [PF][4 arrays][BW]
+    float* stage = smem_raw + RING;   // [PF][4 arrays][BW]
     constexpr int SLOT = 4 * BW;                // floats per staging slot
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -92,7 +108,7 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
         XA[j] = 0.0f;
         XB[j] = 0.0f;
     }
-    for (int i = tid; i < T * 4 * RW + 8; i += BW)
+    for (int i = tid; i < RING; i += BW)
         smem_raw[i] = 0.0f;
 
     // ---- warp-cooperative staging: the 32 columns of a warp x 4 images are 32 chunks of 16 bytes, one per lane
@@ -147,15 +163,34 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
     // the arrival of the level-0 row.  k in 0..3 = step within the group; st = staging slot of this step.
     auto step_body = [&](auto rowmask_tag, const int k, const int y_in, const float* st) {
         constexpr bool ROWMASK = decltype(rowmask_tag)::value;
+        constexpr int NQ = (T + 3) / 4;
+        [[maybe_unused]] float lfq[QG ? NQ * 4 : 1], rtq[QG ? NQ * 4 : 1];
+        if constexpr (QG) {
+            // neighbours of all levels: slot (k+2)&3, columns tid-3 and tid+3, levels 0..T-1 (level t reads ring t-1)
+            const float* nb = smem_raw + ((((k + 2) & 3) * RW + tid + 4) * LS);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 l4 = *reinterpret_cast<const float4*>(nb - 3 * LS + 4 * q);
+                const float4 r4 = *reinterpret_cast<const float4*>(nb + 3 * LS + 4 * q);
+                lfq[4 * q] = l4.x; lfq[4 * q + 1] = l4.y; lfq[4 * q + 2] = l4.z; lfq[4 * q + 3] = l4.w;
+                rtq[4 * q] = r4.x; rtq[4 * q + 1] = r4.y; rtq[4 * q + 2] = r4.z; rtq[4 * q + 3] = r4.w;
+            }
+        }
 #pragma unroll
         for (int t = T; t >= 1; --t) {
             const int rho = y_in - 2 * t;
             const float c = win[t - 1][(k + 2) & 3];   // produced at step s-2
             float up = win[t - 1][(k + 1) & 3];        // s-3
             float dn = win[t - 1][(k + 3) & 3];        // s-1
-            const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * RW + tid;
-            const float lf = row[-3];
-            const float rt = row[3];
+            float lf, rt;
+            if constexpr (QG) {
+                lf = lfq[t - 1];
+                rt = rtq[t - 1];
+            } else {
+                const float* row = sm + ((t - 1) * 4 + ((k + 2) & 3)) * RW + tid;
+                lf = row[-3];
+                rt = row[3];
+            }
             if constexpr (ROWMASK) {
                 dn = (rho + 1) < (H - 1) ? dn : 0.0f;  // (flowconsistency.cu:227)
                 up = rho >= 1 ? up : 0.0f;             // (:232)
@@ -169,8 +204,10 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
             if (t < T) {
                 win[t % T][k & 3] = on;   // (t % T only silences the bounds warning for t == T)
                 uu[t % T][k & 1] = un;
-                if (pub_ok)
-                    sm[((t % T) * 4 + (k & 3)) * RW + tid] = on;
+                if constexpr (!QG) {
+                    if (pub_ok)
+                        sm[((t % T) * 4 + (k & 3)) * RW + tid] = on;
+                }
             } else {
                 // predicated, not branched around: a branch here would end the basic block
                 const int ok = store_col && rho >= r0 && rho < r1;
@@ -182,8 +219,24 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
         const float n_o = st[0];
         win[0][k & 3] = n_o;
         uu[0][k & 1] = st[BW];
-        if (pub_ok)
-            sm[(k & 3) * RW + tid] = n_o;
+        if constexpr (QG) {
+            // publish the T new values of this column (levels 0..T-1) into slot k&3
+            if (pub_ok) {
+                float* pb = smem_raw + (((k & 3) * RW + tid + 4) * LS);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    float4 v;
+                    v.x = win[(4 * q) % T][k & 3];
+                    v.y = 4 * q + 1 < T ? win[(4 * q + 1) % T][k & 3] : 0.0f;
+                    v.z = 4 * q + 2 < T ? win[(4 * q + 2) % T][k & 3] : 0.0f;
+                    v.w = 4 * q + 3 < T ? win[(4 * q + 3) % T][k & 3] : 0.0f;
+                    *reinterpret_cast<float4*>(pb + 4 * q) = v;
+                }
+            }
+        } else {
+            if (pub_ok)
+                sm[(k & 3) * RW + tid] = n_o;
+        }
         XA[2 * T + k] = st[2 * BW];
         XB[2 * T + k] = st[3 * BW];
         so += L;
@@ -263,14 +316,15 @@ static RolledGeom rolled_geom(int T, int BW, int L, int H, int sms)
     return g;
 }
 
-template <int T, int BW, int SYNC>
+template <int T, int BW, int SYNC, bool QG = false>
 static int launch_rolled_impl(const RolledGeom& g, const float* coefA, const float* coefB, const float* u_src,
     float* u_dst, const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st)
 {
     constexpr int PF = rolled_pf(T);
-    const size_t smem = (static_cast<size_t>(T) * 4 * (BW + 8) + 8 + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
+    const size_t ring = QG ? static_cast<size_t>(4) * (BW + 8) * rolled_ls(T) : static_cast<size_t>(T) * 4 * (BW + 8) + 8;
+    const size_t smem = (ring + static_cast<size_t>(PF) * 4 * BW) * sizeof(float);
     static unsigned long long configured = 0;
-    if (const int e = ensure_dynamic_smem(solver_rolled_kernel<T, BW, SYNC>, smem, false, configured))
+    if (const int e = ensure_dynamic_smem(solver_rolled_kernel<T, BW, SYNC, QG>, smem, false, configured))
         return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g.nb, g.nc);
@@ -282,7 +336,7 @@ static int launch_rolled_impl(const RolledGeom& g, const float* coefA, const flo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_rolled_kernel<T, BW, SYNC>, coefA, coefB, u_src, u_dst, o_src,
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_rolled_kernel<T, BW, SYNC, QG>, coefA, coefB, u_src, u_dst, o_src,
         o_dst, W, H, g.chunk_rows, g.first_rows, step, mom);
     count_launch();
     return e == cudaSuccess ? launch_status() : static_cast<int>(e);
@@ -295,6 +349,13 @@ static int launch_rolled(const RolledGeom& g, const float* coefA, const float* c
     if constexpr (T % 2 == 0) {   // the CTA-barrier form (a test hook) is built for the even depths only
         if (!g_stream_pair)
             return launch_rolled_impl<T, BW, 0>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
+    }
+    // quad-gather ring where its shared memory fits (not T = 5..8 with 512-float bands)
+    constexpr bool qg_fits = (static_cast<size_t>(4) * (BW + 8) * rolled_ls(T) + static_cast<size_t>(rolled_pf(T)) * 4 * BW)
+            * sizeof(float) <= 227u * 1024u;
+    if constexpr (qg_fits) {
+        if (g_stream_qg)
+            return launch_rolled_impl<T, BW, 1, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
     }
     return launch_rolled_impl<T, BW, 1>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
 }
