@@ -144,14 +144,16 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  * neighbour-pair named barriers; | 0x20 = per-thread 4-byte staging instead of warp-cooperative 16-byte staging;
  * | 0x40 = vsc_frame_stabilize never takes its fused path; | 0x80 = no programmatic dependent launch
  * anywhere in the library; | (j << 12), j = 1 or 2: main blocked passes always of 8 / always of 10 sweeps
- * (default: 10 on images of at least 0.9 Mpx when that saves passes, else 8); | (k << 8), k = 1..4, forces the band width of the
+ * (default: 8; 10 on images of at least 0.9 Mpx only where that saves enough passes, e.g. 20 sweeps = 2 x 10); | (k << 8), k = 1..4, forces the band width of the
  * blocked kernel (512, 448, 384, 256 floats) instead of the cost model; | 0x8000 = the fully unrolled form of the
  * blocked kernel (stab_solver_stream.cu) instead of the 4-step loop (stab_solver_rolled.cu; needs 16-byte aligned
  * rows; by default it takes every pass except the 10-sweep passes of images of 4 Mpx and more), | 0x4000 = the 4-step
  * loop for those too; | 0x0800 = the sweeps are split into the fewest passes of nearly equal depth, odd depths 3..9
  * included (75 = 3 x 10 + 5 x 9; default: 8- or 10-sweep passes, a 2-sweep remainder merged into the last pass, an odd
  * sweep on its own: measured faster); | ((a + 1) << 16) | ((b + 1) << 22), a, b in 0..62: the first / last row chunk of the 4-step-loop kernel is
- * a / b rows shorter than the others (default 8 / 4).
+ * a / b rows shorter than the others (default 8 / 4); | (1 << 28) = the exchange ring of the 4-step-loop kernel in its scalar
+ * layout (default: quad gather, [slot][column][level], 128-bit accesses); | (1 << 29) = mbarrier arrive / wait hand-off between
+ * neighbouring warps instead of named barriers (measured slower).
  * Process-wide; meant for tests and benchmarks. */
 VSC_API int vsc_set_solver_mode(int mode);
 

@@ -21,6 +21,9 @@ torch.cuda.set_device(0)
 g = torch.Generator(device=dev).manual_seed(0)
 L = V.lib()
 NAMES = {0: "auto", 1: "512", 2: "448", 3: "384", 4: "256"}
+# which vsc_set_solver_mode bit to flip: 28 = ring layout (scalar <-> quad gather), 29 = hand-off (named barriers <-> mbarriers)
+FLIP_BIT = int(sys.argv[1]) if len(sys.argv) > 1 else 28
+FLIPS = (0, 1)
 
 
 def time_solve(pr, tg, wt, out, iters, reps=7):
@@ -47,9 +50,9 @@ for (W, H) in ((1920, 1080), (960, 540), (3840, 2160), (1280, 720), (640, 360)):
         for k in (0, 1, 2, 3, 4):
             if tmain > 8 and k in (1, 2):
                 continue
-            for flip in (0, 1):
+            for flip in FLIPS:
                 # 0x4000: the 4-step-loop kernel for every pass (also the 10-sweep passes of 4K-class images)
-                mode = 2 | 0x4000 | (k << 8) | (((tmain - 6) // 2) << 12) | (flip << 28)
+                mode = 2 | 0x4000 | (k << 8) | (((tmain - 6) // 2) << 12) | (flip << FLIP_BIT)
                 V.check(L.vsc_set_solver_mode(mode))
                 got = V.get_consist_out(pr, tg, wt, 2 * tmain + 3, 0.15, 0.15, pr.clone())
                 ok = torch.equal(got, ref)
