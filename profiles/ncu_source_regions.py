@@ -2,7 +2,7 @@
 often an instruction executed (= which loop nest it sits in), plus the instructions with the most samples.  This is the view
 that showed a third of custom::Correlation's warp time sitting in its per-tile epilogue (round 2).
 
-    python profiles/ncu_source_regions.py gpurun_out/x.ncu-rep [top_n]
+    python profiles/ncu_source_regions.py gpurun_out/x.ncu-rep [top_n [kernel_index]]
 """
 import collections
 import csv
@@ -14,6 +14,7 @@ import sys
 def main():
     path = sys.argv[1]
     top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -21,15 +22,16 @@ def main():
     print("###", rows[0][1][:160])
     hdr = rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    first, prev = [], -1
-    for r in rows[2:]:
-        if len(r) < len(hdr) or not r[0].startswith("0x"):
-            continue
-        a = int(r[0], 16)
-        if a < prev:
-            break
-        prev = a
-        first.append(r)
+    # the page lists the kernels one after the other; a new kernel starts with a "Kernel Name" row
+    kernels, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            kernels.append(cur)
+        elif cur is not None and len(r) >= len(hdr) and r[0].startswith("0x"):
+            cur["rows"].append(r)
+    first = kernels[which]["rows"]
+    print("### kernel", which, "of", len(kernels), ":", kernels[which]["name"][:150])
     S = lambda r: int(r[idx["# Samples"]])
     E = lambda r: int(r[idx["Instructions Executed"]])
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]

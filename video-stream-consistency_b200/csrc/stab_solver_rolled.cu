@@ -36,6 +36,12 @@
 
 #include "vsc_common.cuh"
 
+#ifndef VSC_SOLVER_PREFETCH_NB
+#define VSC_SOLVER_PREFETCH_NB 0
+#endif
+#ifndef VSC_SOLVER_PERMUTE_DEFAULT
+#define VSC_SOLVER_PERMUTE_DEFAULT 0
+#endif
 #ifndef VSC_SOLVER_SPLIT_DEFAULT
 #define VSC_SOLVER_SPLIT_DEFAULT 0
 #endif
@@ -54,6 +60,7 @@ extern std::atomic<int> g_stream_band;           // 0 = cost model; 1..4 force a
 std::atomic<int> g_stream_rolled = 1;            // 0: never use this kernel (vsc_set_solver_mode | 0x8000), 1: auto, 2: always (| 0x4000)
 std::atomic<int> g_stream_edge_top = -1;         // rows by which the first / last row chunk is shorter than the others (-1: default)
 std::atomic<int> g_stream_edge_bot = -1;
+std::atomic<int> g_stream_permute = VSC_SOLVER_PERMUTE_DEFAULT;   // 1: warps of one scheduler own adjacent column blocks (| 1 << 30 flips it)
 std::atomic<int> g_stream_split = VSC_SOLVER_SPLIT_DEFAULT;   // 1: mbarrier arrive / wait hand-off between neighbouring warps (| 1 << 29 flips it)
 std::atomic<int> g_stream_qg = VSC_SOLVER_QG_DEFAULT;   // 1: exchange ring in the quad-gather layout (vsc_set_solver_mode | 1 << 28 flips it)
 
@@ -69,7 +76,7 @@ template <int T, int BW, int SYNC, bool QG = false>
 __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __restrict__ coefA,
     const float* __restrict__ coefB, const float* __restrict__ u_src, float* __restrict__ u_dst,
     const float* __restrict__ o_src, float* __restrict__ o_dst, int W, int H, int chunk_rows, int first_rows, float step,
-    float mom)
+    float mom, int permute)
 {
     constexpr int HALO = rolled_halo(T);
     constexpr int S = BW - 2 * HALO;   // columns stored per band
@@ -94,7 +101,18 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
     constexpr int SLOT = 4 * BW;                // floats per staging slot
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int tid = threadIdx.x;
+    // Column block of a warp.  permute: the warps of one scheduler (hardware warp slot % 4; a CTA owns the SM, so slot =
+    // warp index) take ADJACENT column blocks, so that a warp's exchange partners sit on its own scheduler except at
+    // three block boundaries: when a warp waits at the pair barrier, the partner it waits for inherits its issue slots.
+    int tid = threadIdx.x;
+    if (permute) {
+        const int pw = tid >> 5, sch = pw & 3;
+        int before = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            before += j < sch ? (BW / 32 - j + 3) / 4 : 0;
+        tid = (before + (pw >> 2)) * 32 + (tid & 31);
+    }
     const int L = 3 * W;
     const int g0 = blockIdx.x * S - HALO;
     const int gi = g0 + tid;
@@ -213,7 +231,20 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
 
     // One step: levels T..1 (level T first: it reads the window row the arrival of step k+... never touches), then
     // the arrival of the level-0 row.  k in 0..3 = step within the group; st = staging slot of this step.
-    auto step_body = [&](auto rowmask_tag, const int k, const int y_in, const float* st, const int sidx) {
+    // neighbours of all levels for step k: slot (k+2)&3, columns tid-3 and tid+3, levels 0..T-1 (level t reads ring t-1)
+    [[maybe_unused]] auto load_nb = [&](const int k, float* lfq, float* rtq) {
+        constexpr int NQ = (T + 3) / 4;
+        const float* nb = smem_raw + ((((k + 2) & 3) * RW + tid + 4) * LS);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 l4 = *reinterpret_cast<const float4*>(nb - 3 * LS + 4 * q);
+            const float4 r4 = *reinterpret_cast<const float4*>(nb + 3 * LS + 4 * q);
+            lfq[4 * q] = l4.x; lfq[4 * q + 1] = l4.y; lfq[4 * q + 2] = l4.z; lfq[4 * q + 3] = l4.w;
+            rtq[4 * q] = r4.x; rtq[4 * q + 1] = r4.y; rtq[4 * q + 2] = r4.z; rtq[4 * q + 3] = r4.w;
+        }
+    };
+    auto step_body = [&](auto rowmask_tag, const int k, const int y_in, const float* st, const int sidx,
+                         const float* pre = nullptr) {
         constexpr bool ROWMASK = decltype(rowmask_tag)::value;
         constexpr int NQ = (T + 3) / 4;
         if constexpr (SYNC == 2) {
@@ -222,14 +253,14 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
         }
         [[maybe_unused]] float lfq[QG ? NQ * 4 : 1], rtq[QG ? NQ * 4 : 1];
         if constexpr (QG) {
-            // neighbours of all levels: slot (k+2)&3, columns tid-3 and tid+3, levels 0..T-1 (level t reads ring t-1)
-            const float* nb = smem_raw + ((((k + 2) & 3) * RW + tid + 4) * LS);
+            if (pre != nullptr) {   // (compile-time: the interval loaded both steps' neighbours up front)
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const float4 l4 = *reinterpret_cast<const float4*>(nb - 3 * LS + 4 * q);
-                const float4 r4 = *reinterpret_cast<const float4*>(nb + 3 * LS + 4 * q);
-                lfq[4 * q] = l4.x; lfq[4 * q + 1] = l4.y; lfq[4 * q + 2] = l4.z; lfq[4 * q + 3] = l4.w;
-                rtq[4 * q] = r4.x; rtq[4 * q + 1] = r4.y; rtq[4 * q + 2] = r4.z; rtq[4 * q + 3] = r4.w;
+                for (int i = 0; i < NQ * 4; ++i) {
+                    lfq[i] = pre[i];
+                    rtq[i] = pre[NQ * 4 + i];
+                }
+            } else {
+                load_nb(k, lfq, rtq);
             }
         }
 #pragma unroll
@@ -312,9 +343,20 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
                 const int rq = slot + k - 2 < 0 ? PF - 2 : slot + k - 2;
                 request(y_first + k + PF - 2, rq, false);
                 request(y_first + k + PF - 1, rq + 1, true);
-                step_body(rowmask_tag, k, y_first + k, st + k * SLOT, base + k);
-                if (!EDGE || base + k + 1 < nsteps)
-                    step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT, base + k + 1);
+                if constexpr (QG && SYNC != 2 && VSC_SOLVER_PREFETCH_NB) {
+                    // both steps' neighbour quads are visible since the barrier that opened the interval: the second
+                    // step's loads are in flight while the first step computes
+                    constexpr int NQ4 = (T + 3) / 4 * 4;
+                    float nb1[2 * NQ4];
+                    load_nb(k + 1, nb1, nb1 + NQ4);
+                    step_body(rowmask_tag, k, y_first + k, st + k * SLOT, base + k);
+                    if (!EDGE || base + k + 1 < nsteps)
+                        step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT, base + k + 1, nb1);
+                } else {
+                    step_body(rowmask_tag, k, y_first + k, st + k * SLOT, base + k);
+                    if (!EDGE || base + k + 1 < nsteps)
+                        step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT, base + k + 1);
+                }
                 // my copies of the next interval's two rows: all but the (PF-4)/2 youngest groups
                 asm volatile("cp.async.wait_group %0;" ::"n"((PF - 4) / 2) : "memory");
                 ring_sync();
@@ -395,7 +437,7 @@ static int launch_rolled_impl(const RolledGeom& g, const float* coefA, const flo
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, solver_rolled_kernel<T, BW, SYNC, QG>, coefA, coefB, u_src, u_dst, o_src,
-        o_dst, W, H, g.chunk_rows, g.first_rows, step, mom);
+        o_dst, W, H, g.chunk_rows, g.first_rows, step, mom, static_cast<int>(g_stream_permute));
     count_launch();
     return e == cudaSuccess ? launch_status() : static_cast<int>(e);
 }
