@@ -54,7 +54,8 @@ for (W, H) in ((160, 96), (45, 37), (400, 64)):
     wt = torch.rand((H, W, 3), device=dev, generator=g) * 2
     # (round 2: the default is the 4-step loop; 0x8000 = the fully unrolled form, 0x4000 forces the loop, edge fields)
     for mode in (1, 2, 0x12, 0x22, 0x82, 0x1002, 0x2002, 0x2022, 0x8002, 0x8012, 0xA002, 0x6002, 2 | (17 << 16) | (11 << 22),
-                 0x0802, 0x2802):   # balanced plan: odd pass depths
+                 0x0802, 0x2802,   # balanced plan: odd pass depths
+                 2 | (1 << 28), 0x2002 | (1 << 28), 2 | (1 << 30), 0x1302 | (1 << 30)):   # scalar ring, permuted column blocks
         V.check(L.vsc_set_solver_mode(mode))
         for iters in (1, 9, 21):
             V.get_consist_out(pr, tg, wt, iters, 0.15, 0.15, pr.clone())

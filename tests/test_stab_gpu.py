@@ -403,13 +403,11 @@ def test_blocked_solver_is_bit_identical_to_unblocked(V, dev, W, H, iters):
         # ..., the fully unrolled form of the kernel (0x8000; the default is the 4-step loop), row chunks of equal
         # height (edge fields 1/1 = 0 rows shorter) and much shorter first / last chunks (16 / 10 rows); 0x0800 = the
         # balanced plan (passes of nearly equal depth: the odd depths 3, 5, 7, 9 of the 4-step-loop kernel); bit 28 flips
-        # the layout of the exchange ring (scalar <-> quad gather), bit 29 the hand-off between neighbouring warps (named
-        # barriers <-> mbarrier arrive / wait), bit 30 the assignment of column blocks to warps
+        # the layout of the exchange ring (scalar <-> quad gather), bit 30 the assignment of column blocks to warps
         modes = (2, 2 | 0x10, 2 | 0x20, 2 | 0x80, 2 | 0x1000, 2 | 0x2000, 2 | 0x2020, 2 | 0x8000, 2 | 0x8010, 2 | 0xA000,
                  2 | 0x6000, 2 | 0x4010, 2 | 0x0800, 2 | 0x1800, 2 | 0x2800,
                  2 | (1 << 16) | (1 << 22), 2 | 0x2000 | (17 << 16) | (11 << 22),
                  2 | (1 << 28), 2 | 0x1000 | (1 << 28), 2 | 0x2000 | (1 << 28), 2 | 0x0800 | (1 << 28), 2 | 0x4000 | 0x0100 | (1 << 28),
-                 2 | (1 << 29), 2 | 0x1000 | (1 << 29), 2 | 0x2000 | (1 << 29), 2 | 0x1100 | (1 << 29), 2 | 0x1400 | (1 << 29),
                  2 | (1 << 30), 2 | 0x1200 | (1 << 30), 2 | 0x2000 | (1 << 30), 2 | 0x10 | (1 << 30))
         for mode in modes:
             assert L.vsc_set_solver_mode(mode) == 0

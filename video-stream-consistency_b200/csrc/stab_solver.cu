@@ -26,9 +26,6 @@
 #ifndef VSC_SOLVER_QG_DEFAULT
 #define VSC_SOLVER_QG_DEFAULT 1
 #endif
-#ifndef VSC_SOLVER_SPLIT_DEFAULT
-#define VSC_SOLVER_SPLIT_DEFAULT 0
-#endif
 #ifndef VSC_SOLVER_PERMUTE_DEFAULT
 #define VSC_SOLVER_PERMUTE_DEFAULT 0
 #endif
@@ -185,7 +182,7 @@ int solver_stream_pass(int T, const float* coefA, const float* coefB, const floa
 // implemented in stab_solver_rolled.cu: the same passes with a 4-step loop (16-byte aligned rows); false = not applicable
 bool solver_rolled_pass(int T, const float* coefA, const float* coefB, const float* u_src, float* u_dst,
     const float* o_src, float* o_dst, int W, int H, float step, float mom, cudaStream_t st, int* rc);
-extern std::atomic<int> g_stream_rolled, g_stream_qg, g_stream_split, g_stream_permute;
+extern std::atomic<int> g_stream_rolled, g_stream_qg, g_stream_permute;
 
 std::atomic<int> g_solver_mode = 0;  // 0 auto, 1 unblocked sweeps only, 2 temporally blocked passes whenever iters >= 4
 extern std::atomic<bool> g_stream_pair, g_stream_coop;  // stab_solver_stream.cu: variants of the blocked kernel
@@ -355,7 +352,7 @@ extern "C" int vsc_consist_solve(const float* crntPr, const float* prevStabWarp,
 extern "C" int vsc_set_solver_mode(int mode)
 {
     const int lo = mode & 0xFFFF;
-    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0xC000) == 0xC000 || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2)
+    if (mode < 0 || (lo & 0xF) > 2 || (lo & 0xC000) == 0xC000 || ((lo >> 8) & 7) > 4 || ((lo >> 12) & 3) > 2 || ((mode >> 29) & 1))
         return VSC_E_INVALID;
     g_solver_mode = lo & 0xF;
     g_stream_pair = (lo & 0x10) == 0;
@@ -368,7 +365,6 @@ extern "C" int vsc_set_solver_mode(int mode)
     g_plan_balanced = (lo & 0x0800) != 0;
     g_stream_qg = ((mode >> 28) & 1) ? !VSC_SOLVER_QG_DEFAULT : VSC_SOLVER_QG_DEFAULT;
     g_stream_permute = ((mode >> 30) & 1) ? !VSC_SOLVER_PERMUTE_DEFAULT : VSC_SOLVER_PERMUTE_DEFAULT;
-    g_stream_split = ((mode >> 29) & 1) ? !VSC_SOLVER_SPLIT_DEFAULT : VSC_SOLVER_SPLIT_DEFAULT;
     g_stream_edge_top = ((mode >> 16) & 0x3F) - 1;   // 0 = default
     g_stream_edge_bot = ((mode >> 22) & 0x3F) - 1;
     return VSC_OK;

@@ -25,8 +25,9 @@
 //     of two steps is one basic block;
 //   * the first and the last row chunk may be shorter than the others (the CTAs that run the masked copy are the
 //     slowest of the one-wave grid).
-//   * quad-gather exchange ring (QG, default) and the mbarrier hand-off experiment (SYNC == 2): see the comments at
-//     solver_rolled_kernel and at `mbar` below.
+//   * quad-gather exchange ring (QG, default): see the comment at solver_rolled_kernel.  (An mbarrier arrive / wait
+//     hand-off between neighbouring warps with a step of slack was measured 10-50 % slower than the named barriers and
+//     removed again: profiles/r2_solver_split_sweep.txt.)
 // Results are bit-identical to stab_solver_stream.cu and to the unblocked sweeps (same arithmetic per value, only
 // the schedule differs): tests/test_stab_gpu.py::test_blocked_solver_is_bit_identical_to_unblocked.
 //
@@ -41,9 +42,6 @@
 #endif
 #ifndef VSC_SOLVER_PERMUTE_DEFAULT
 #define VSC_SOLVER_PERMUTE_DEFAULT 0
-#endif
-#ifndef VSC_SOLVER_SPLIT_DEFAULT
-#define VSC_SOLVER_SPLIT_DEFAULT 0
 #endif
 #ifndef VSC_SOLVER_QG_DEFAULT
 #define VSC_SOLVER_QG_DEFAULT 1
@@ -61,7 +59,6 @@ std::atomic<int> g_stream_rolled = 1;            // 0: never use this kernel (vs
 std::atomic<int> g_stream_edge_top = -1;         // rows by which the first / last row chunk is shorter than the others (-1: default)
 std::atomic<int> g_stream_edge_bot = -1;
 std::atomic<int> g_stream_permute = VSC_SOLVER_PERMUTE_DEFAULT;   // 1: warps of one scheduler own adjacent column blocks (| 1 << 30 flips it)
-std::atomic<int> g_stream_split = VSC_SOLVER_SPLIT_DEFAULT;   // 1: mbarrier arrive / wait hand-off between neighbouring warps (| 1 << 29 flips it)
 std::atomic<int> g_stream_qg = VSC_SOLVER_QG_DEFAULT;   // 1: exchange ring in the quad-gather layout (vsc_set_solver_mode | 1 << 28 flips it)
 
 // QG ("quad gather"): the exchange ring is laid out [slot][column][level] (LS floats per column) instead of
@@ -92,12 +89,6 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
     constexpr int RING = QG ? 4 * RW * LS : T * 4 * RW + 8;   // floats
     float* sm = smem_raw + 4;
     float* stage = smem_raw + RING;   // [PF][4 arrays][BW]
-    // SYNC == 2: split arrive / wait hand-off of the exchange ring.  Warp w signals mbarrier [s & 3][w] after it has
-    // published step s; a warp waits for its two neighbours' signals of step s-2 right before it reads their values at
-    // step s.  Between a signal and the wait that needs it lies a whole step of work, so a warp seldom blocks (with the
-    // named barriers a quarter of all warp samples sat at the barrier: profiles/r2_solver_qg_ncu.txt).  Four mbarriers
-    // per warp: a warp is never more than two steps ahead of a neighbour, i.e. at most one phase per mbarrier.
-    __shared__ __align__(8) unsigned long long mbar[SYNC == 2 ? 4 * (BW / 32) : 1];
     constexpr int SLOT = 4 * BW;                // floats per staging slot
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -140,12 +131,6 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
     }
     for (int i = tid; i < RING; i += BW)
         smem_raw[i] = 0.0f;
-    if constexpr (SYNC == 2) {
-        if (tid < 4 * (BW / 32)) {
-            const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(mbar + tid));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
-        }
-    }
 
     // ---- warp-cooperative staging: the 32 columns of a warp x 4 images are 32 chunks of 16 bytes, one per lane
     // (lane l copies columns [g0 + 32*warp + 4*(l%8), +4) of image l/8); chunks lie entirely inside or outside the
@@ -182,42 +167,8 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
 
     constexpr int NW = BW / 32;
     const int warp = tid >> 5;
-    const unsigned mb0 = static_cast<unsigned>(__cvta_generic_to_shared(mbar));
-    // wait for the neighbours' publication of global step s2 (>= 0)
-    [[maybe_unused]] auto nb_wait = [&](const int s2) {
-        const unsigned par = static_cast<unsigned>(s2 >> 2) & 1u;
-        const unsigned slot = mb0 + 8u * static_cast<unsigned>((s2 & 3) * NW);
-#pragma unroll
-        for (int side = -1; side <= 1; side += 2) {
-            const int nw = warp + side;
-            if (nw >= 0 && nw < NW) {
-                const unsigned a = slot + 8u * static_cast<unsigned>(nw);
-                asm volatile(
-                    "{\n"
-                    ".reg .pred p;\n"
-                    "NBW_%=:\n"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                    "@p bra NBD_%=;\n"
-                    "bra NBW_%=;\n"
-                    "NBD_%=:\n"
-                    "}\n" ::"r"(a),
-                    "r"(par)
-                    : "memory");
-            }
-        }
-    };
-    // my warp has published global step s
-    [[maybe_unused]] auto nb_signal = [&](const int s) {
-        __syncwarp();
-        if ((tid & 31) == 0) {
-            const unsigned a = mb0 + 8u * static_cast<unsigned>((s & 3) * NW + warp);
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-        }
-    };
     auto ring_sync = [&]() {
-        if constexpr (SYNC == 2) {
-            __syncwarp();   // the staged rows of the next interval: every lane waited for its own copies
-        } else if constexpr (SYNC == 1 && NW <= 16) {
+        if constexpr (SYNC == 1 && NW <= 16) {
             const int first = (warp & 1) ? warp + 1 : warp;   // boundary ids: left = warp, right = warp + 1
             const int second = (warp & 1) ? warp : warp + 1;
             if (first >= 1 && first <= NW - 1)
@@ -243,14 +194,9 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
             rtq[4 * q] = r4.x; rtq[4 * q + 1] = r4.y; rtq[4 * q + 2] = r4.z; rtq[4 * q + 3] = r4.w;
         }
     };
-    auto step_body = [&](auto rowmask_tag, const int k, const int y_in, const float* st, const int sidx,
-                         const float* pre = nullptr) {
+    auto step_body = [&](auto rowmask_tag, const int k, const int y_in, const float* st, const float* pre = nullptr) {
         constexpr bool ROWMASK = decltype(rowmask_tag)::value;
         constexpr int NQ = (T + 3) / 4;
-        if constexpr (SYNC == 2) {
-            if (sidx >= 2)
-                nb_wait(sidx - 2);   // the neighbours' values of step s-2 (slot (k+2)&3) are about to be read
-        }
         [[maybe_unused]] float lfq[QG ? NQ * 4 : 1], rtq[QG ? NQ * 4 : 1];
         if constexpr (QG) {
             if (pre != nullptr) {   // (compile-time: the interval loaded both steps' neighbours up front)
@@ -327,8 +273,6 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
         XA[2 * T + k] = st[2 * BW];
         XB[2 * T + k] = st[3 * BW];
         so += L;
-        if constexpr (SYNC == 2)
-            nb_signal(sidx);
     };
 
     // One group of four steps = two barrier intervals.  slot = staging slot of the group's first step (a multiple
@@ -343,19 +287,19 @@ __global__ void __launch_bounds__(BW, 1) solver_rolled_kernel(const float* __res
                 const int rq = slot + k - 2 < 0 ? PF - 2 : slot + k - 2;
                 request(y_first + k + PF - 2, rq, false);
                 request(y_first + k + PF - 1, rq + 1, true);
-                if constexpr (QG && SYNC != 2 && VSC_SOLVER_PREFETCH_NB) {
+                if constexpr (QG && VSC_SOLVER_PREFETCH_NB) {
                     // both steps' neighbour quads are visible since the barrier that opened the interval: the second
                     // step's loads are in flight while the first step computes
                     constexpr int NQ4 = (T + 3) / 4 * 4;
                     float nb1[2 * NQ4];
                     load_nb(k + 1, nb1, nb1 + NQ4);
-                    step_body(rowmask_tag, k, y_first + k, st + k * SLOT, base + k);
+                    step_body(rowmask_tag, k, y_first + k, st + k * SLOT);
                     if (!EDGE || base + k + 1 < nsteps)
-                        step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT, base + k + 1, nb1);
+                        step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT, nb1);
                 } else {
-                    step_body(rowmask_tag, k, y_first + k, st + k * SLOT, base + k);
+                    step_body(rowmask_tag, k, y_first + k, st + k * SLOT);
                     if (!EDGE || base + k + 1 < nsteps)
-                        step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT, base + k + 1);
+                        step_body(rowmask_tag, k + 1, y_first + k + 1, st + (k + 1) * SLOT);
                 }
                 // my copies of the next interval's two rows: all but the (PF-4)/2 youngest groups
                 asm volatile("cp.async.wait_group %0;" ::"n"((PF - 4) / 2) : "memory");
@@ -455,10 +399,6 @@ static int launch_rolled(const RolledGeom& g, const float* coefA, const float* c
             * sizeof(float) <= 227u * 1024u;
     if constexpr (qg_fits) {
         if (g_stream_qg) {
-            if constexpr (T == 8 || T == 10 || T == 6) {   // the split hand-off is built for the main depths only
-                if (g_stream_split)
-                    return launch_rolled_impl<T, BW, 2, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
-            }
             return launch_rolled_impl<T, BW, 1, true>(g, coefA, coefB, u_src, u_dst, o_src, o_dst, W, H, step, mom, st);
         }
     }
