@@ -1,4 +1,5 @@
 D=gpurun_out/qg
 mkdir -p $D
-VSC_B200_LIB=$PWD/video-stream-consistency_b200/lib/libvsc_b200_pfnb.so timeout 400 python profiles/sweep_solver_qg.py 28 > $D/sweep_pfnb.txt 2>&1
-cat $D/sweep_pfnb.txt
+( timeout 600 python -m pytest tests/test_stab_gpu.py -m gpu -q -x -k "blocked" ) > $D/pytest.log 2>&1; tail -2 $D/pytest.log
+timeout 400 python profiles/sweep_solver_qg.py 28 > $D/sweep_tail.txt 2>&1
+cat $D/sweep_tail.txt
