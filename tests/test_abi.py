@@ -83,6 +83,18 @@ def test_kernel_selection_words_are_validated(V):
     for bad in (-1, 5, 6, 0x1001):
         assert L.vsc_set_warp_mode(bad) == -1, hex(bad)
     assert L.vsc_set_warp_mode(0) == 0
+    for ok in (0, 1, 2, 3, 4, 5, 6, 7):   # 5 / 6: shared-row tiles (64 / 32 wide), 7: quad form of the channel-split kernel
+        assert L.vsc_set_correlation_mode(ok) == 0, ok
+    for bad in (-1, 8, 0x100):
+        assert L.vsc_set_correlation_mode(bad) == -1, bad
+    assert L.vsc_set_correlation_mode(0) == 0
+    # solver: low nibble 0..2, flags, band (k << 8, k <= 4), depth (j << 12, j <= 2), edge fields, bit 28 (ring layout),
+    # bit 30 (column blocks); bit 29 is not assigned
+    for ok in (0, 1, 2, 2 | 0x10, 2 | 0x0800, 2 | 0x2400, 2 | 0x8000, 2 | (17 << 16) | (11 << 22), 2 | (1 << 28), 2 | (1 << 30)):
+        assert L.vsc_set_solver_mode(ok) == 0, hex(ok)
+    for bad in (-1, 3, 2 | 0x0500, 2 | 0x3000, 2 | 0xC000, 2 | (1 << 29)):
+        assert L.vsc_set_solver_mode(bad) == -1, hex(bad)
+    assert L.vsc_set_solver_mode(0) == 0
 
 
 def test_workspace_sizes(V):
