@@ -313,9 +313,28 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
 
     out8 = torch.empty((H, W, 4), device=dev, dtype=torch.uint8)
 
-    def step_resident(t):
+    # Two streams (default; --no-overlap-ops = one stream): the custom ops of a frame (its flow network) run on a second
+    # stream.  The flow of frame t does not depend on the stabilized output of frame t-1, so ops(t+1) may run while frame
+    # t is being stabilized (the solver passes leave issue slots and, at level 1, half of every SM free): stabilization(t)
+    # waits for ops(t), and ops(t+1) waits for stabilization(t-1) -- one frame of look-ahead, no more.  Every op and
+    # every stabilization call goes through the same C-ABI entry points as before; only the stream argument differs.
+    overlap = bool(wl["corr"]) and not args.no_overlap_ops
+    ops_stream = torch.cuda.Stream(device=dev) if overlap else None
+    stab_done = []
+
+    def step_resident(t, two_streams=True):
         nonlocal last, cons
-        run_ops(V, sets)
+        if ops_stream is not None and two_streams:
+            cur = torch.cuda.current_stream()
+            if len(stab_done) >= 2:
+                ops_stream.wait_event(stab_done[-2])
+            with torch.cuda.stream(ops_stream):
+                run_ops(V, sets)
+                ev = torch.cuda.Event()
+                ev.record(ops_stream)
+            cur.wait_event(ev)
+        else:
+            run_ops(V, sets)
         if lowres:
             V.check(L.vsc_bilinear(dptr(d_flf), fw, fh, 3, dptr(upf), W, H, 3, stream()))
             V.check(L.vsc_bilinear(dptr(d_flb), fw, fh, 3, dptr(upb), W, H, 3, stream()))
@@ -324,6 +343,11 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
                           workspace=ws)   # flow channel count is taken from the flow tensors
         V.check(L.vsc_f32x3_to_rgba8(dptr(cons), dptr(out8), W, H, stream()))
         last, cons = cons, last
+        if ops_stream is not None and two_streams:
+            ev2 = torch.cuda.Event()
+            ev2.record(torch.cuda.current_stream())
+            stab_done.append(ev2)
+            del stab_done[:-2]
 
     def barrier():
         torch.cuda.synchronize()
@@ -352,6 +376,19 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
     barrier()
     launches = V.launch_count() - n0
     ms_res = e0.elapsed_time(e1)
+    # the same K steps with everything on ONE stream, for the record (`one_stream` in the JSON line)
+    ms_one = None
+    if ops_stream is not None:
+        torch.cuda.current_stream().wait_stream(ops_stream)
+        step_resident(1 + Wm + K, two_streams=False)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for t in range(K):
+            step_resident(2 + Wm + K + t, two_streams=False)
+        f1.record()
+        barrier()
+        ms_one = f0.elapsed_time(f1)
 
     # ---------------- end-to-end arm: host frame buffers through the pipeline object ----------------
     st = V.Stabilizer(W, H, flow_c)
@@ -378,6 +415,8 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
         net = ((fw + 63) // 64 * 64, (fh + 63) // 64 * 64)
         net_in = [torch.empty((net[1], net[0], 4), device=dev, dtype=torch.uint8) for _ in range(3)]
 
+    e2e_done = []
+
     def step_e2e(t):
         if net:
             for i in range(3):
@@ -386,9 +425,23 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
             st.step_flow_files(flow_dir, 1 + t % NFLO, outs[t & 1])
             st.prefetch_flow_files(flow_dir, 1 + (t + 1) % NFLO)
         else:
-            with torch.cuda.stream(ext):  # custom ops share the pipeline's compute stream
-                run_ops(V, sets)
+            if ops_stream is not None:   # ops(t) on the second stream; see step_resident
+                if len(e2e_done) >= 2:
+                    ops_stream.wait_event(e2e_done[-2])
+                with torch.cuda.stream(ops_stream):
+                    run_ops(V, sets)
+                    ev = torch.cuda.Event()
+                    ev.record(ops_stream)
+                ext.wait_event(ev)
+            else:
+                with torch.cuda.stream(ext):  # custom ops share the pipeline's compute stream
+                    run_ops(V, sets)
             st.step(d_flf, d_flb, outs[t & 1])
+            if ops_stream is not None:
+                ev2 = torch.cuda.Event()
+                ev2.record(ext)
+                e2e_done.append(ev2)
+                del e2e_done[:-2]
         st.push_frame(ho[(t + 2) % NFRAMES], hp[(t + 2) % NFRAMES])
 
     for t in range(3):
@@ -577,7 +630,7 @@ def run_workload(args, name, K, Wm, rank, world, dev, sustained_s=0.0, sample_cl
     del d_o, d_p, last, cons, ws, sets, f_full, sa_out, out8, outs
     torch.cuda.empty_cache()
     return dict(ms_res=ms_res, ms_e2e=ms_e2e, launches=launches, clocks=clk, roofline=roofline, e2e=e2e,
-                sustained=sustained, h2d_gbs=h2d_gbs)
+                sustained=sustained, h2d_gbs=h2d_gbs, ms_one=ms_one)
 
 
 def bench_ours(args, rank, world):
@@ -615,7 +668,15 @@ def bench_ours(args, rank, world):
             "gpu_launches": int(launches),
             "clocks": r["clocks"],
             "roofline": r["roofline"],
+            "pipeline": ("two streams: the custom ops of frame t+1 run on a second stream while frame t is stabilized "
+                         "(stabilization(t) waits for ops(t), ops(t+1) for stabilization(t-1)); both arms of this line"
+                         if (WORKLOADS[args.workload]["corr"] and not args.no_overlap_ops)
+                         else "one stream: custom ops, then stabilization"),
         }
+        if r.get("ms_one") is not None and world == 1:
+            result["one_stream"] = {"value": aggregate_fps(1, K, r["ms_one"]), "unit": "frames/s",
+                                    "ms_per_step": r["ms_one"] / K,
+                                    "note": "the same steps with custom ops and stabilization on ONE stream (--no-overlap-ops)"}
         if r["sustained"]:
             result["sustained"] = r["sustained"]
         if cpu:
@@ -631,6 +692,8 @@ def bench_ours(args, rank, world):
                    "value": aggregate_fps(1, Ke, x["ms_res"]), "unit": "frames/s", "ms_per_step": x["ms_res"] / Ke,
                    "e2e": dict(value=aggregate_fps(1, Ke, x["ms_e2e"]), unit="frames/s", **x["e2e"]),
                    "gpu_launches": int(x["launches"]), "clocks": x["clocks"],
+                   **({"one_stream": {"value": aggregate_fps(1, Ke, x["ms_one"]), "unit": "frames/s"}}
+                      if x.get("ms_one") is not None else {}),
                    "roofline": {k: x["roofline"][k] for k in ("kernel", "bound", "achieved", "frac", "traffic", "dram_frac",
                                                               "us_per_launch", "fused_stage_a", "unblocked_sweep",
                                                               "custom_ops")}}
@@ -762,6 +825,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short 4k-stab / 4k-dense runs (N = 1 only)")
     ap.add_argument("--no-numa-bind", action="store_true", help="keep the launcher's CPU affinity")
+    ap.add_argument("--no-overlap-ops", action="store_true",
+                    help="custom ops and stabilization on ONE stream (default: the ops of frame t+1 run on a second stream "
+                         "while frame t is stabilized)")
     ap.add_argument("--sustained", type=float, default=3.0,
                     help="seconds of back-to-back device-resident frames for the `sustained` record (N = 1; 0 = off)")
     ap.add_argument("--solver-mode", type=lambda x: int(x, 0), default=0, help="vsc_set_solver_mode value (A/B runs)")
