@@ -151,7 +151,7 @@ VSC_API int vsc_consist_solve(const float* crntPr, const float* prevStabWarp, co
  * loop for those too; | 0x0800 = the sweeps are split into the fewest passes of nearly equal depth, odd depths 3..9
  * included (75 = 3 x 10 + 5 x 9; default: 8- or 10-sweep passes, a 2-sweep remainder merged into the last pass, an odd
  * sweep on its own: measured faster); | ((a + 1) << 16) | ((b + 1) << 22), a, b in 0..62: the first / last row chunk of the 4-step-loop kernel is
- * a / b rows shorter than the others (default 8 / 4); | (1 << 28) = the exchange ring of the 4-step-loop kernel in its scalar
+ * a / b rows shorter than the others (default 12 / 6); | (1 << 28) = the exchange ring of the 4-step-loop kernel in its scalar
  * layout (default: quad gather, [slot][column][level], 128-bit accesses); | (1 << 30) = the warps of one scheduler own adjacent
  * column blocks.
  * Process-wide; meant for tests and benchmarks. */

@@ -346,7 +346,7 @@ static RolledGeom rolled_geom(int T, int BW, int L, int H, int sms)
     if (nc < 1) nc = 1;
     // the first / last chunk run the masked copy for 3T / 2T steps: shorter by default (profiles/r2_solver_sweep_pairs_edges.txt)
     const int et = g_stream_edge_top, eb = g_stream_edge_bot;
-    int top = et >= 0 ? et : 8, bot = eb >= 0 ? eb : 4;
+    int top = et >= 0 ? et : 12, bot = eb >= 0 ? eb : 6;   // (12 / 6 since the quad-gather ring: profiles/r2_solver_qg_sweep.txt)
     if (nc < 3 || H < nc * (2 * T + top + bot)) top = bot = 0;
     // H = (mid - top) + (nc - 2) * mid + last,  last <= mid - bot
     g.chunk_rows = (H + top + bot + nc - 1) / nc;
