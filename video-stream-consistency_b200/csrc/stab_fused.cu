@@ -12,6 +12,10 @@
 // so the results are bit-identical to calling those one by one.
 #include "stab_device.cuh"
 
+#ifndef VSC_STAGE_A_MINBLOCKS
+#define VSC_STAGE_A_MINBLOCKS 4   // 64 registers: 8 CTAs of 128 threads per SM (3 -> 85 registers, 6 CTAs: measured)
+#endif
+
 namespace vsc {
 
 // One thread per VALUE (pixel, channel) of a row, not per pixel: the image is interleaved HWC, so consecutive
@@ -226,7 +230,7 @@ __device__ __forceinline__ void stage_a_finish(const StageATaps& t, float cp, fl
 }
 
 template <int PIPE>
-__global__ void __launch_bounds__(256, PIPE == 2 ? 2 : 4) stage_a_prep_rows_kernel(StageAPtrs P, int flowC,
+__global__ void __launch_bounds__(256, PIPE == 2 ? 2 : VSC_STAGE_A_MINBLOCKS) stage_a_prep_rows_kernel(StageAPtrs P, int flowC,
     float alpha, float beta, float gamma, float step, float* __restrict__ coefA, float* __restrict__ coefB,
     float* __restrict__ pr1, float* __restrict__ tg1, float* __restrict__ wt1, int W, int H, int rows)
 {
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(256, PIPE == 2 ? 2 : 4) stage_a_prep_rows_kern
 }
 
 // vsc_stage_a_fused (adapCmbPr / consWt written out, no solver set-up) as a row walk with the flow prefetched
-__global__ void __launch_bounds__(256, 4) stage_a_rows_kernel(StageAPtrs P, int flowC, float alpha, float beta,
+__global__ void __launch_bounds__(256, VSC_STAGE_A_MINBLOCKS) stage_a_rows_kernel(StageAPtrs P, int flowC, float alpha, float beta,
     float gamma, float* __restrict__ adapCmbIn, float* __restrict__ adapCmbPr, float* __restrict__ consWt, int W, int H,
     int rows)
 {
